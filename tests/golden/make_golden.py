@@ -1,0 +1,289 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Runs only where a reference checkout exists ($SHIPPINGENV_REF or /root/reference).
+Every array written here is the output of the reference's own
+``Environment.step/reset/sample_action`` (``shipping/environment.py``),
+``MCTSAgent._rollout`` (``agents/mcts.py:211-238``) or ``preprocess_state``
+(``utils/preprocessing.py:25-62``), driven through ``oracle/ref_harness.py`` with
+``shipping.environment.random`` rebound to the Philox shim.  The fixtures pin
+``oracle/shipenv_oracle.c`` (tests, ``-m "not gpu"``) and the CUDA path (``-m gpu``).
+"""
+import collections
+import hashlib
+import os
+import random as stock_random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle.ref_harness import (RefBatch, import_reference, ref_rollout, f64_bits,  # noqa: E402
+                                NONE_PORT, POLICY, EXT_CARGO, EXT_FUEL)
+from oracle.philox_shim import PhiloxRandom  # noqa: E402
+
+SEED = 0x5EED
+STOCK_FUEL = [20, 14, 18, 12, 16]   # random.seed(2024) draw, SURVEY App. C
+STOCK_CARGO = [10, 11, 13, 20, 18]
+
+
+def run(batch, actions, max_steps, auto_reset, word0=0):
+    """Step ``batch`` over actions[T, N]; returns the per-step trace as arrays."""
+    T, N = actions.shape
+    tr = dict(
+        actions=actions.astype(np.int16),
+        pos=np.zeros((T, N, 4), np.uint8), cargo=np.zeros((T, N), np.int32),
+        fuel=np.zeros((T, N), np.uint64), reward=np.zeros((T, N), np.float64),
+        done=np.zeros((T, N), np.uint8), status=np.zeros((T, N), np.uint8),
+        reset=np.zeros((T, N), np.uint8), taken=np.zeros((T, N), np.int16),
+        clock=np.zeros((T, N), np.uint32),
+    )
+    p0, c0, f0 = batch.states()
+    tr["init_pos"], tr["init_cargo"], tr["init_fuel"] = p0, c0, f0
+    tr["init_clock"] = batch.clock.copy()
+    for t in range(T):
+        o = batch.step(actions[t], max_steps=max_steps, auto_reset=auto_reset, word0=word0)
+        p, c, f = batch.states()
+        tr["pos"][t], tr["cargo"][t], tr["fuel"][t] = p, c, f
+        for k in ("reward", "done", "status", "reset", "taken"):
+            tr[k][t] = o[k]
+        tr["clock"][t] = batch.clock
+    tr["max_steps"] = np.int64(max_steps)
+    tr["auto_reset"] = np.int64(auto_reset)
+    tr["word0"] = np.int64(word0)
+    tr["env_id_base"] = np.uint64(batch.base)
+    tr["seed"] = np.uint64(batch.shim.seed)
+    return tr
+
+
+def port_meta(batch):
+    e = batch.envs[0]
+    return dict(
+        port_xy=np.array(e.port_positions, np.uint8).reshape(-1, 2),
+        port_fuel=np.array(e.port_fuel, np.uint8), port_cargo=np.array(e.port_cargo, np.uint8),
+        passable=(e.np_game != 0).astype(np.uint8),
+    )
+
+
+def bfs_next_move(passable, src, dst):
+    """First move of a shortest passable path src->dst (moves N,E,S,W); None if unreachable."""
+    moves = [(0, -1), (-1, 0), (0, 1), (1, 0)]
+    W, H = passable.shape
+    prev = {tuple(dst): None}
+    q = collections.deque([tuple(dst)])
+    while q:  # search backwards from dst so prev[] gives the forward step
+        cur = q.popleft()
+        if cur == tuple(src):
+            break
+        for k, (dx, dy) in enumerate(moves):
+            nb = (cur[0] - dx, cur[1] - dy)  # nb --move k--> cur
+            if 0 <= nb[0] < W and 0 <= nb[1] < H and passable[nb] and nb not in prev:
+                prev[nb] = k
+                q.append(nb)
+    return prev.get(tuple(src))
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def main():
+    ns = import_reference()
+    PORTS = ns.consts.DEFAULT_PORTS
+
+    # --- self-check: the reference imported here is the program SURVEY App. C hashed ----
+    ns.envmod.random = stock_random
+    stock_random.seed(2024)
+    e = ns.envmod.Environment(ns.map_path)
+    h_map = hashlib.sha256(e.np_game.astype(np.uint8).tobytes()).hexdigest()
+    assert h_map == "49253a2cbaf1c86b8ae4f4b400c082eac97da02718ee2237b1734783a12622e8", h_map
+    for p in PORTS:
+        e.add_port(list(p))
+    assert e.port_fuel == STOCK_FUEL and e.port_cargo == STOCK_CARGO
+    h = hashlib.sha256()
+    e.reset()
+    h.update(repr((e.ship_position, e.origin_port_index, e.destination_port_index)).encode())
+    n = 0
+    while n < 1000:
+        a = e.sample_action()
+        try:
+            _, r, d, _ = e.step(a)
+        except Exception:
+            continue
+        n += 1
+        rec = (a[0], a[1], tuple(e.ship_position), float(e.fuel).hex(), e.cargo,
+               e.origin_port_index, e.destination_port_index, float(r).hex(), d)
+        h.update(repr(rec).encode())
+        if d:
+            e.reset()
+            h.update(repr((e.ship_position, e.origin_port_index, e.destination_port_index)).encode())
+    print("stock-RNG trajectory sha256:", h.hexdigest())
+
+    rng = np.random.default_rng(1234)
+
+    # --- default map ------------------------------------------------------------------
+    b = RefBatch(ns, 1, SEED, PORTS, STOCK_FUEL, STOCK_CARGO)
+    meta = port_meta(b)
+    assert hashlib.sha256(meta["passable"].tobytes()).hexdigest() == \
+        "2774b34f9bc98e9806ad059529d413d6af2685fe5270e3817ebe19e5c6c5b0d0"
+    np_game_before = ns.envmod.Environment(ns.map_path).np_game.astype(np.uint8)
+    save("default_map", np_game=np_game_before, ports=np.array(PORTS, np.uint8),
+         stock_fuel=np.array(STOCK_FUEL, np.uint8), stock_cargo=np.array(STOCK_CARGO, np.uint8),
+         **{k: v for k, v in meta.items() if k == "passable"})
+
+    # --- port stock drawn by add_port under the shim ----------------------------------
+    stock = {}
+    for seed in (SEED, 0, 0xDEADBEEFCAFEF00D):
+        bb = RefBatch(ns, 1, seed, PORTS)
+        stock[f"fuel_{seed:x}"] = np.array(bb.envs[0].port_fuel, np.uint8)
+        stock[f"cargo_{seed:x}"] = np.array(bb.envs[0].port_cargo, np.uint8)
+    save("port_stock", **stock)
+
+    # --- G1: uniform random moves, auto-reset, truncation at 300 ----------------------
+    b = RefBatch(ns, 64, SEED, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.reset()
+    save("g1_moves", **run(b, rng.integers(0, 4, (640, 64)), 300, True), **port_meta(b))
+
+    # --- G2: on-device policy (sample_action retry loop), truncation at 500 -----------
+    b = RefBatch(ns, 64, SEED, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.reset()
+    tr = run(b, np.full((640, 64), POLICY), 500, True)
+    obs = b.observe()
+    save("g2_policy", **tr, obs=obs, **port_meta(b))
+
+    # --- G3: the whole flat action space incl. rejected actions -----------------------
+    b = RefBatch(ns, 64, SEED, PORTS, STOCK_FUEL, STOCK_CARGO, env_id_base=(1 << 33) + 5)
+    b.reset()
+    T, N = 400, 64
+    kind = rng.random((T, N))
+    acts = rng.integers(0, 4, (T, N))
+    acts = np.where(kind > 0.55, rng.integers(4, 9, (T, N)), acts)
+    acts = np.where(kind > 0.65, rng.integers(9, 59, (T, N)), acts)
+    acts = np.where(kind > 0.80, rng.integers(59, 259, (T, N)), acts)
+    junk = rng.choice(np.array([-2, -300, 259, 260, 1000, EXT_CARGO, EXT_CARGO + 7, EXT_CARGO + 300,
+                                EXT_FUEL, EXT_FUEL + 3, EXT_FUEL + 8191, 0x3FFF, -32768, POLICY]), (T, N))
+    acts = np.where(kind > 0.93, junk, acts)
+    save("g3_mixed", **run(b, acts, 200, True), **port_meta(b))
+
+    # --- G4: navigator -- take cargo, sail the shortest route, deliver; no auto-reset --
+    b = RefBatch(ns, 32, SEED ^ 0xABCDEF, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.reset()
+    T, N = 700, 32
+    passable = port_meta(b)["passable"].astype(bool)
+    acts = np.zeros((T, N), np.int64)
+    tr_parts = []
+    for t in range(T):
+        row = np.zeros(N, np.int64)
+        for i, e in enumerate(b.envs):
+            cur = e._get_current_port_idx()
+            if cur is not None and e.cargo == 0:
+                row[i] = 4 + 5 + min(e.port_cargo[cur], 3 + (i % 17))       # TAKE_CARGO
+            elif cur is not None and e.fuel < 60 and (t + i) % 3 == 0:
+                row[i] = 4 + 5 + 50 + e.port_fuel[cur]                        # TAKE_FUEL
+            else:
+                k = bfs_next_move(passable, e.ship_position,
+                                  e.port_positions[e.destination_port_index])
+                row[i] = k if k is not None and (t * 7 + i) % 11 else int(rng.integers(0, 4))
+        acts[t] = row
+        tr_parts.append(run(b, row[None, :], 0, False))
+    tr = {k: np.concatenate([p[k] for p in tr_parts]) for k in
+          ("actions", "pos", "cargo", "fuel", "reward", "done", "status", "reset", "taken", "clock")}
+    for k in ("init_pos", "init_cargo", "init_fuel", "init_clock", "max_steps", "auto_reset",
+              "word0", "env_id_base", "seed"):
+        tr[k] = tr_parts[0][k]
+    print("  navigator: arrivals =", int((tr["reward"] > 5).sum()), " dones =", int(tr["done"].sum()),
+          " min fuel =", np.frombuffer(tr["fuel"][-1].tobytes(), np.float64).min())
+    save("g4_navigator", **tr, **port_meta(b))
+
+    # --- G5: all-water synthetic map: edges, off-map rejections, 2 ports --------------
+    import cv2
+    img = np.full((355, 533), 255, np.uint8)
+    water_png = "/tmp/shipenv_allwater.png"
+    cv2.imwrite(water_png, img)
+    for tag, ports, acts_fn in (
+        ("g5_edges_moves", [[0, 0], [99, 99], [0, 99], [50, 50]],
+         lambda: rng.integers(0, 4, (500, 48))),
+        ("g5_edges_policy", [[0, 0], [1, 0]], lambda: np.full((500, 48), POLICY)),
+    ):
+        b = RefBatch(ns, 48, SEED + 1, ports, map_path=water_png)
+        b.reset()
+        tr = run(b, acts_fn(), 120, True, word0=0)
+        print(f"  {tag}: off-map rejections =", int((tr['status'] == 1).sum()),
+              " arrivals =", int((tr["reward"] > 5).sum()))
+        save(tag, **tr, **port_meta(b))
+
+    # --- G6: crafted states (each env starts from a hand-built state) -----------------
+    crafted = [
+        # x, y, origin, dest, cargo, fuel, actions...
+        (62, 72, 4, 1, 0, 0.5, [1, 1, 0, 2]),            # out of fuel: done, move proceeds, fuel < 0
+        (62, 72, 4, 1, 0, 0.95, [1, 1, 1, 1]),           # fuel ~ cost: done depends on the jitter
+        (41, 40, 0, NONE_PORT, 0, 200, [POLICY, POLICY, POLICY, POLICY]),  # policy selects a port
+        (41, 40, NONE_PORT, NONE_PORT, 0, 200, [0, 4, 5, 2]),   # move w/o dest (2), select ok
+        (50, 50, 0, NONE_PORT, 0, 200, [POLICY, 3, 9, 60]),     # policy w/o dest off port -> 2
+        (61, 72, 4, 1, 60, 200, [1, 3, 1, 3]),           # cargo > capacity: loss every move
+        (61, 72, 4, 1, 1, 200, [1, 3, 1, 3]),            # cargo 1
+        (60, 22, 4, 1, 7, 200, [0, 1, 2, 3]),            # sits on its destination: blocked-move arrival
+        (60, 23, 4, 1, 9, 150.25, [0, 0, 2, 0]),         # sail onto the destination with cargo
+        (49, 72, 3, 0, 5, 0, [POLICY, POLICY, 2, 2]),    # fuel == 0 at port, cargo != 0: sample crash (9)
+        (49, 72, 3, 0, 0, 0, [POLICY, POLICY, POLICY, 2]),  # fuel == 0 but cargo == 0: takes cargo
+        (62, 72, 4, 1, 0, 200, [4 + 4, 4 + 1, 4 + 5, 4 + 0]),  # select origin (4), ok, range.. (flat 9 = cargo 0 -> 6)
+        (62, 72, 4, 1, 0, 200, [9 + 18, 9 + 19, 59 + 16, 59 + 17]),  # stock bounds 18/16 at port 4
+        (10, 10, 4, 1, 0, 200, [9 + 1, 59 + 1, 4 + 2, 4 + 7]),       # not at port (5), select range (3)
+        (62, 72, 4, 1, 2_000_000, 1e6, [1, 3, 1, 3]),    # large cargo: int(beta*cargo) in fp64
+        (62, 72, 4, 1, 0, -3.5, [1, 1, 59 + 5, 1]),      # negative fuel keeps stepping
+    ]
+    N = len(crafted)
+    b = RefBatch(ns, N, SEED + 2, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.clock[:] = np.arange(N, dtype=np.uint32) * 65536 * 3 + 17
+    for i, c in enumerate(crafted):
+        b.set_state(i, *c[:6])
+    acts = np.array([c[6] for c in crafted]).T  # [4, N]
+    acts = np.concatenate([acts, rng.integers(0, 4, (60, N))])
+    tr = run(b, acts, 0, False)
+    print("  crafted status rows:\n", tr["status"][:4])
+    save("g6_crafted", **tr, **port_meta(b))
+
+    # --- G7: word0 offset (facade: sample_action() then step()) -----------------------
+    b = RefBatch(ns, 16, SEED + 3, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.reset()
+    save("g7_word0", **run(b, rng.integers(0, 4, (64, 16)), 0, False, word0=1), **port_meta(b))
+
+    # --- G8: rollouts = the reference's MCTSAgent._rollout ----------------------------
+    R, S = 48, 6
+    b = RefBatch(ns, R, SEED, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.reset()
+    for t in range(10):
+        b.step(np.full(R, POLICY), 0, False)
+    # make some roots short on fuel so that rollouts terminate by `done`
+    for i in range(0, R, 6):
+        b.envs[i].fuel = 3.0 + i
+    rp, rc, rf = b.states()
+    out = dict(root_pos=rp, root_cargo=rc, root_fuel=rf)
+    for L in (100, 25):
+        ret = np.zeros((R, S), np.uint64)
+        fin_pos = np.zeros((R, S, 4), np.uint8)
+        fin_cargo = np.zeros((R, S), np.int32)
+        fin_fuel = np.zeros((R, S), np.uint64)
+        for r in range(R):
+            for s in range(S):
+                total, copy = ref_rollout(ns, b.shim, b.envs[r], 1000 + r, s, L)
+                ret[r, s] = f64_bits(total)
+                fin_pos[r, s] = (copy.ship_position[0], copy.ship_position[1],
+                                 copy.origin_port_index, copy.destination_port_index)
+                fin_cargo[r, s] = copy.cargo
+                fin_fuel[r, s] = f64_bits(copy.fuel)
+        out[f"ret_L{L}"], out[f"fin_pos_L{L}"] = ret, fin_pos
+        out[f"fin_cargo_L{L}"], out[f"fin_fuel_L{L}"] = fin_cargo, fin_fuel
+    out["root_id_base"] = np.uint64(1000)
+    out["seed"] = np.uint64(SEED)
+    save("g8_rollouts", **out, **port_meta(b))
+
+
+if __name__ == "__main__":
+    main()
