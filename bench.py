@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py -- env-steps/s of the batched ShippingEnv step on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 2,097,152 envs
+per GPU (16M over 8), default map, 5 default ports, uniform random move actions, auto-reset on
+done or after 1,000 steps, Philox seed 0x5EED, global env ids rank * 2^21 + i (weak scaling, no
+collective on the step path).  One "step" = one shipenv_step launch over every env of the rank.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM and L2
+flushed between steps; `e2e` goes through the same C-ABI call with the step's actions coming
+from pinned host memory and reward + done/reset masks going back to it, copies inside the timed
+region.  `--impl reference` times the CPU oracle port (oracle/shipenv_oracle.c, the reference
+is pure Python and cannot travel to the GPU box) on all host cores on the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 1 << 21
+SEED = 0x5EED
+MAX_STEPS = 1000
+BYTES_PER_STEP = 46          # 16+4+2 read, 16+4+4 written, + 3 ballot bits
+ACTION_POOL = 32             # distinct pre-generated action vectors, cycled
+FLUSH_BYTES = 256 << 20      # > 126 MB L2
+METRIC = "env-steps/sec (whole box)"
+
+
+def world():
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "default_map.npz"))
+    return z["passable"]
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region through NVML
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.ok:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: the oracle port on host threads (ctypes releases the GIL inside the C call)
+# ---------------------------------------------------------------------------------------------
+def cpu_steps_per_s(n_envs, budget_s, threads, min_steps=4):
+    """Random-move auto-reset stepping of `n_envs` envs with the C oracle on `threads` threads."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import lib as orc
+    from shippingenv_b200.batched import DEFAULT_PORTS, DEFAULT_PORT_FUEL, DEFAULT_PORT_CARGO
+    o = orc.Oracle(world(), DEFAULT_PORTS, DEFAULT_PORT_FUEL, DEFAULT_PORT_CARGO)
+    ships, clock = np.zeros(n_envs, orc.SHIP_DTYPE), np.zeros(n_envs, np.uint32)
+    o.reset(ships, clock, SEED)
+    rng = np.random.default_rng(1234)
+    pool = [rng.integers(0, 4, n_envs).astype(np.int16) for _ in range(8)]
+    bounds = np.linspace(0, n_envs, threads + 1).astype(np.int64)
+    reward = np.zeros(n_envs, np.float64)
+    done = np.zeros(n_envs, np.uint8)
+    import ctypes as C
+    L = orc.lib()
+
+    def work(k, acts):
+        lo, hi = int(bounds[k]), int(bounds[k + 1])
+        L.orc_step(C.byref(o.w), C.c_void_p(ships.ctypes.data + 16 * lo), C.c_void_p(clock.ctypes.data + 4 * lo),
+                   C.c_void_p(acts.ctypes.data + 2 * lo), C.c_void_p(reward.ctypes.data + 8 * lo),
+                   C.c_void_p(done.ctypes.data + lo), None, None, None, C.c_uint64(SEED), C.c_uint64(lo),
+                   C.c_int64(hi - lo), C.c_int(MAX_STEPS), C.c_int(1), C.c_uint32(0))
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda k: work(k, pool[0]), range(threads)))      # warm-up step
+        t0 = time.perf_counter()
+        steps = 0
+        while steps < min_steps or time.perf_counter() - t0 < budget_s:
+            list(ex.map(lambda k: work(k, pool[steps % len(pool)]), range(threads)))
+            steps += 1
+        dt = time.perf_counter() - t0
+    return n_envs * steps / dt, steps, dt
+
+
+def run_reference(args):
+    """The reference arm: the path's CPU implementation on all host cores, same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    import ctypes as C
+    from oracle import lib as orc
+    from shippingenv_b200.batched import DEFAULT_PORTS, DEFAULT_PORT_FUEL, DEFAULT_PORT_CARGO
+    threads = os.cpu_count() or 1
+    n = ENVS_PER_GPU * args.gpus
+    sample = min(n, ENVS_PER_GPU)          # each step: one pass over a 2M-env sample of the workload
+    o = orc.Oracle(world(), DEFAULT_PORTS, DEFAULT_PORT_FUEL, DEFAULT_PORT_CARGO)
+    ships, clock = np.zeros(sample, orc.SHIP_DTYPE), np.zeros(sample, np.uint32)
+    o.reset(ships, clock, SEED)
+    rng = np.random.default_rng(1234)
+    pool = [rng.integers(0, 4, sample).astype(np.int16) for _ in range(8)]
+    reward, done = np.zeros(sample, np.float64), np.zeros(sample, np.uint8)
+    bounds = np.linspace(0, sample, threads + 1).astype(np.int64)
+    L = orc.lib()
+
+    def work(k, acts):
+        lo, hi = int(bounds[k]), int(bounds[k + 1])
+        L.orc_step(C.byref(o.w), C.c_void_p(ships.ctypes.data + 16 * lo), C.c_void_p(clock.ctypes.data + 4 * lo),
+                   C.c_void_p(acts.ctypes.data + 2 * lo), C.c_void_p(reward.ctypes.data + 8 * lo),
+                   C.c_void_p(done.ctypes.data + lo), None, None, None, C.c_uint64(SEED), C.c_uint64(lo),
+                   C.c_int64(hi - lo), C.c_int(MAX_STEPS), C.c_int(1), C.c_uint32(0))
+
+    steps = min(args.steps, 256)            # bounded: the whole run stays within a few minutes
+    warm = min(args.warmup, 8)
+    with ThreadPoolExecutor(threads) as ex:
+        for t in range(warm):
+            list(ex.map(lambda k: work(k, pool[t % 8]), range(threads)))
+        t0 = time.perf_counter()
+        for t in range(steps):
+            list(ex.map(lambda k: work(k, pool[t % 8]), range(threads)))
+        dt = time.perf_counter() - t0
+    value = sample * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} envs x {steps} steps, oracle/shipenv_oracle.c (C restatement of the "
+                                   "pure-Python reference, which cannot travel to this box) on all host threads"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(gpus):
+    return {"workload": f"{ENVS_PER_GPU} envs/GPU x {gpus} GPU(s) (BASELINE configs[2]: 16M envs over 8 GPUs), "
+                        "default 100x100 map, 5 default ports, uniform random N/E/S/W actions (int16, pre-generated on "
+                        "device), auto-reset on done or 1000 steps, Philox seed 0x5EED",
+            "envs_per_gpu": ENVS_PER_GPU, "max_steps": MAX_STEPS,
+            "l2": "flushed between timed steps (256 MiB fill, outside the per-step event pairs)",
+            "bytes_per_env_step": BYTES_PER_STEP}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from shippingenv_b200 import BatchedEnvironment, launch_count, unpack_bits
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_size != args.gpus:
+        if world_size == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.envs
+    env = BatchedEnvironment(n, passable=world(), seed=SEED, device=dev, env_id_base=rank * n,
+                             max_steps=MAX_STEPS, auto_reset=True)
+    env.reset()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = [torch.randint(0, 4, (n,), generator=gen, device=dev, dtype=torch.int16) for _ in range(ACTION_POOL)]
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident: per-step CUDA events on the launching stream, L2 flushed in between ----
+    for t in range(W):
+        env.step(pool[t % ACTION_POOL])
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    launches0 = launch_count()
+    with ClockSampler(local) as clocks:
+        for t in range(K):
+            flush.fill_(t & 255)
+            starts[t].record()
+            env.step(pool[t % ACTION_POOL])
+            stops[t].record()
+        barrier()
+    launches = launch_count() - launches0
+    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = sum(per_step_ms)
+    err = int(env.error_bits.ne(0).sum().item())
+
+    # ---- L2-warm variant: K back-to-back launches between two events (reported separately) ----
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for t in range(K):
+        env.step(pool[t % ACTION_POOL])
+    e1.record()
+    barrier()
+    warm_ms = e0.elapsed_time(e1)
+
+    # ---- end to end: actions from pinned host memory, reward + masks back to pinned host ----
+    h_act = [torch.randint(0, 4, (n,), dtype=torch.int16).pin_memory() for _ in range(4)]
+    d_act = torch.empty(n, dtype=torch.int16, device=dev)
+    nw = (n + 31) // 32
+    h_reward = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(nw, dtype=torch.int32).pin_memory()
+    h_reset = torch.empty(nw, dtype=torch.int32).pin_memory()
+    Ke = max(8, min(K, 64))
+
+    def e2e_step(t):
+        d_act.copy_(h_act[t % 4], non_blocking=True)
+        r = env.step(d_act)
+        h_reward.copy_(r.reward, non_blocking=True)
+        h_done.copy_(r.done_bits, non_blocking=True)
+        h_reset.copy_(r.reset_bits, non_blocking=True)
+
+    for t in range(3):
+        e2e_step(t)
+    barrier()
+    e0.record()
+    for t in range(Ke):
+        e2e_step(t)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    checksum = float(h_reward.sum())
+
+    # ---- max over ranks ----
+    times = torch.tensor([total_ms, warm_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, warm_ms, e2e_ms = times.tolist()
+
+    if rank == 0:
+        n_total = n * world_size
+        value = n_total * K / (total_ms * 1e-3)
+        kernel_ms = total_ms / K
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = n * BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+        if os.path.exists(prof):
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world_size, "steps": K,
+            "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world_size),
+            "value_l2_warm": n_total * K / (warm_ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "shipenv::step_kernel<false>",
+                         "algorithmic_bytes_per_launch": n * BYTES_PER_STEP},
+            "e2e": {"value": n_total * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n + 8 * nw, "steps": Ke,
+                    "what": "shipenv_step via BatchedEnvironment.step: int16 actions from pinned host memory, "
+                            "f32 reward + done/reset masks to pinned host memory, one stream"},
+            "gpu_launches": launches, "clocks": clocks.summary(),
+            "rejected_actions_last_step": err, "reward_checksum": checksum,
+        }
+        if world_size == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            v, s, dt = cpu_steps_per_s(1 << 18, args.cpu_seconds, threads)
+            v1, s1, dt1 = cpu_steps_per_s(1 << 16, min(3.0, args.cpu_seconds), 1)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                "single_thread_value": v1,
+                "sample": f"{1 << 18} envs x {s} steps ({dt:.1f} s) of the same workload with oracle/shipenv_oracle.c "
+                          f"on {threads} threads; the reference itself is pure Python (~6e4 steps/s/core, BASELINE.md)"}
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    import __graft_entry__ as entry
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        entry.build()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,188 @@
+/* shipenv.h -- C ABI of the B200-native batched ShippingEnv step.
+ *
+ * The reference (VanshJP/ShippingEnv) is pure Python and has no FFI of its own; these
+ * entry points are the surface a maintainer binds with ctypes in place of the Python
+ * methods cited on each function (see INTEGRATION.md for the stub).  Citations are
+ * file:line in the reference checkout.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SHIPENV_E_* code otherwise;
+ *     shipenv_last_error() gives the message of the calling thread's last failure;
+ *   - `ships`, `clock`, `actions` and every output pointer are DEVICE pointers owned by
+ *     the caller (torch tensors: tensor.data_ptr()); the library allocates nothing per
+ *     call.  Arguments of shipenv_set_* are HOST pointers (tiny tables, copied);
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     all work is enqueued on it, nothing synchronises;
+ *   - a context belongs to one device; calls on one context must not race.
+ *
+ * Batched contract ("Batched contract"):
+ *   env i of a launch has global id env_id_base + i.  Draws of one accepted step come
+ *   from the Philox4x32-10 cell (seed, env id, clock[i]), words word0, word0+1, ...;
+ *   clock = episode << 16 | step_in_episode; a reset moves it to the next multiple of
+ *   65536.  Rejected actions (status != 0) change nothing and consume nothing.
+ */
+#ifndef SHIPENV_H_
+#define SHIPENV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHIPENV_ABI_VERSION 1
+#define SHIPENV_MAX_PORTS 32      /* ports per world (reference default: 5, utils/constants.py:57-63) */
+#define SHIPENV_MAX_DIM 256       /* map side; coordinates are u8 (reference: 100, shipping/environment.py:29) */
+#define SHIPENV_MAX_CAPACITY 255  /* Initial.MAX_CARGO_CAPACITY upper bound (reference: 50) */
+#define SHIPENV_NONE_PORT 255     /* origin/dest == None (shipping/environment.py:40-41) */
+#define SHIPENV_MAX_TRIES 32      /* policy / rollout: consecutive rejected draws before giving up */
+
+/* Flat action index (int16), utils/preprocessing.py:111-137, P = number of ports:
+ *   [0,4)            MOVE   N,E,S,W = (0,-1),(-1,0),(0,1),(1,0)   (shipping/type.py:13-16)
+ *   [4,4+P)          SELECT_PORT a-4
+ *   [4+P,4+P+50)     TAKE_CARGO amount a-(4+P)       (amount 0 is rejected)
+ *   [4+P+50,4+P+250) TAKE_FUEL  amount a-(4+P+50)
+ *   -1               policy: sample_action() until a step is accepted (shipping/environment.py:245-263,
+ *                    agents/mcts.py:228-236)
+ *   [0x4000,0x6000)  TAKE_CARGO amount a-0x4000  (amounts the flat space cannot express)
+ *   [0x6000,0x8000)  TAKE_FUEL  amount a-0x6000
+ *   anything else    rejected, SHIPENV_ST_UNKNOWN */
+#define SHIPENV_ACT_POLICY (-1)
+#define SHIPENV_ACT_EXT_CARGO 0x4000
+#define SHIPENV_ACT_EXT_FUEL 0x6000
+#define SHIPENV_N_CARGO_ACTIONS 50
+#define SHIPENV_N_FUEL_ACTIONS 200
+
+/* Per-env status: one code per exception of the reference (shipping/environment.py). */
+enum {
+  SHIPENV_ST_OK = 0,
+  SHIPENV_ST_OFF_MAP = 1,      /* ValueError("Move is out of range")                            :284 */
+  SHIPENV_ST_NO_DEST = 2,      /* Exception("Cannot move without destination port")             :276 */
+  SHIPENV_ST_SEL_RANGE = 3,    /* IndexError("Port index is out of range")                      :269 */
+  SHIPENV_ST_SEL_ORIGIN = 4,   /* Exception("Destination port must be different from current one") :267 */
+  SHIPENV_ST_NOT_AT_PORT = 5,  /* Exception("Not currently at port")                            :343,352 */
+  SHIPENV_ST_BAD_AMOUNT = 6,   /* ValueError("Invalid fuel amount")                             :346,355 */
+  SHIPENV_ST_UNKNOWN = 7,      /* ValueError("Action category unknown")                         :374 */
+  SHIPENV_ST_NO_PORTS = 8,     /* Exception("No ports available")                               :360 */
+  SHIPENV_ST_SAMPLE_CRASH = 9  /* sample_action with fuel == 0 at a port indexes a float        :163 */
+};
+
+enum {
+  SHIPENV_E_ARG = -1,      /* bad argument (message says which) */
+  SHIPENV_E_CUDA = -2,     /* a CUDA runtime call failed */
+  SHIPENV_E_STATE = -3     /* context not ready (no map / no ports) */
+};
+
+/* step flags */
+#define SHIPENV_F_AUTO_RESET 1u   /* reset an env in the step that ends its episode (done or truncated) */
+
+/* One ship, 16 bytes, moved as a single 128-bit load/store.  Mirrors the attributes
+ * Environment keeps per ship (shipping/environment.py:37-41). */
+typedef struct {
+  uint8_t x, y;            /* ship_position = [x, y]; np_game[x, y]                 */
+  uint8_t origin, dest;    /* origin/destination_port_index; 255 = None             */
+  int32_t cargo;           /* Environment.cargo (true cargo, not the state-dict copy of fuel) */
+  double fuel;             /* Environment.fuel (float64 after the first water move)  */
+} shipenv_ship;
+
+/* Initial / Reward / Penalty (shipping/environment.py:8-26). */
+typedef struct {
+  int32_t cargo0;          /* Initial.CARGO = 0 */
+  int32_t capacity;        /* Initial.MAX_CARGO_CAPACITY = 50 */
+  double fuel0;            /* Initial.FUEL = 200 */
+  double r_deliver;        /* Reward.CARGO_DELIVER = 2 (per unit) */
+  double r_arrive;         /* Reward.REACH_DESTINATION = 10 */
+  double r_closer;         /* Reward.CLOSER_TO_DESTINATION = 2 */
+  double r_take_fuel;      /* Reward.TAKE_FUEL = 0.05 */
+  double r_take_cargo;     /* Reward.TAKE_CARGO = 0.05 */
+  double p_no_fuel;        /* Penalty.RUN_OUT_OF_FUEL = -10 */
+  double p_ground;         /* Penalty.MOVE_ON_GROUND = -5 */
+  double p_water;          /* Penalty.MOVE_ON_WATER = -1 */
+  double p_loss;           /* Penalty.CARGO_LOSS = -3 (per unit) */
+  double p_farther;        /* Penalty.FARTHER_FROM_DESTINATION = -2 */
+  double p_use_fuel;       /* Penalty.USE_FUEL = -0.0001 */
+} shipenv_consts;
+
+/* Outputs of one batched step; every pointer is a device pointer or NULL (= not wanted).
+ * Bit i%32 of word i/32 belongs to env i; words hold ceil(n/32) entries. */
+typedef struct {
+  float *reward_f32;       /* [n] reward, computed in fp64 in the reference's order, rounded once */
+  double *reward_f64;      /* [n] the fp64 reward itself */
+  uint32_t *done_bits;     /* `done` returned by Environment.step (out of fuel, :288-290) */
+  uint32_t *reset_bits;    /* env was auto-reset in this step (done, or step count reached max_steps) */
+  uint32_t *error_bits;    /* status != 0 */
+  uint8_t *status;         /* [n] SHIPENV_ST_* */
+  int16_t *taken;          /* [n] the action executed (differs from the input only for policy actions) */
+  float *obs;              /* [n, 6+4P] preprocess_state row of the state AFTER the step (and reset) */
+  double *ep_return;       /* [n] running return of the current episode (read-modify-write) */
+  double *stats;           /* [6] episode statistics accumulated at episode end (needs ep_return):
+                              sum return, sum return^2, sum length, episodes, max return, min return */
+} shipenv_step_io;
+
+typedef struct shipenv_ctx shipenv_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int shipenv_abi_version(void);
+const char *shipenv_last_error(void);
+/* Environment.__init__ (shipping/environment.py:29-43): one context per (process, device). */
+int shipenv_ctx_create(int device, shipenv_ctx **out);
+int shipenv_ctx_destroy(shipenv_ctx *ctx);
+
+/* ---- world: replaces Environment._initialize_map / add_port state ------------------ */
+/* passable[x*H + y] != 0  <=>  np_game[x, y] != Entity.GROUND (shipping/environment.py:45-55,
+ * :293).  The JPEG decode/resize/threshold stays on the host (cv2), only the grid comes here. */
+int shipenv_set_map(shipenv_ctx *ctx, const uint8_t *passable, int W, int H);
+/* port_positions / port_fuel / port_cargo (shipping/environment.py:33-35, :57-65). */
+int shipenv_set_ports(shipenv_ctx *ctx, const uint8_t *px, const uint8_t *py, const uint8_t *pfuel,
+                      const uint8_t *pcargo, int P);
+int shipenv_set_consts(shipenv_ctx *ctx, const shipenv_consts *c);  /* NULL = reference defaults */
+int shipenv_get_consts(shipenv_ctx *ctx, shipenv_consts *out);
+int shipenv_obs_width(shipenv_ctx *ctx);                            /* 6 + 4P, utils/preprocessing.py:53-62 */
+int shipenv_num_actions(shipenv_ctx *ctx);                          /* 4+P+50+200, utils/preprocessing.py:93-108 */
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* Environment.reset (shipping/environment.py:227-243) for every env whose mask bit is set
+ * (mask_bits == NULL: all).  Draws from cell (seed, env, clock) then starts a new episode. */
+int shipenv_reset(shipenv_ctx *ctx, shipenv_ship *ships, uint32_t *clock, uint64_t seed,
+                  uint64_t env_id_base, int64_t n, const uint32_t *mask_bits, void *stream);
+
+/* Environment.step (shipping/environment.py:359-376) and everything it calls (:265-357),
+ * for n envs; policy actions also run sample_action (:245-263).  max_steps == 0 disables
+ * truncation; word0 is the first word of the cell to use (0 unless the caller already
+ * drew from it, e.g. sample_action() followed by step() on the N=1 facade). */
+int shipenv_step(shipenv_ctx *ctx, shipenv_ship *ships, uint32_t *clock, const int16_t *actions,
+                 const shipenv_step_io *io, uint64_t seed, uint64_t env_id_base, int64_t n,
+                 int max_steps, uint32_t flags, uint32_t word0, void *stream);
+
+/* Environment.sample_action (shipping/environment.py:245-263), one call per env, drawing
+ * from word0 of the cell (seed, env, clock).  words_used[i] (nullable) = words consumed;
+ * status[i] (nullable) = 0 or SHIPENV_ST_SAMPLE_CRASH / SHIPENV_ST_NO_PORTS. */
+int shipenv_sample_action(shipenv_ctx *ctx, const shipenv_ship *ships, const uint32_t *clock,
+                          int16_t *actions_out, uint8_t *words_used, uint8_t *status,
+                          uint64_t seed, uint64_t env_id_base, int64_t n, uint32_t word0, void *stream);
+
+/* _build_state + preprocess_state (shipping/environment.py:202-225, utils/preprocessing.py:25-62)
+ * as float32 rows [n, 6+4P] (the dtype the DQN feeds its network, agents/dqn.py:198). */
+int shipenv_observe(shipenv_ctx *ctx, const shipenv_ship *ships, float *obs, int64_t n, void *stream);
+
+/* MCTSAgent._rollout (agents/mcts.py:211-238) from copies of R root ships, S rollouts each,
+ * at most L accepted steps.  Rollout (r, s) draws one continuous word stream from the cell
+ * (seed ^ "ROLL"<<32, root_id_base + r, s).  returns[r*S+s] is the fp64 sum of step rewards;
+ * final/steps/status are nullable ([R*S] each). */
+int shipenv_rollout(shipenv_ctx *ctx, const shipenv_ship *roots, int64_t R, int S, int L,
+                    double *returns, shipenv_ship *final, int32_t *steps, uint8_t *status,
+                    uint64_t seed, uint64_t root_id_base, void *stream);
+
+/* ---- host-side helpers (no GPU) ------------------------------------------------------ */
+/* Philox4x32-10 block (the word-stream definition). */
+void shipenv_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* The two random.randint(5, 20) draws of add_port (shipping/environment.py:63-64) for port
+ * `port_index`, from the cell (seed ^ "PORT"<<32, 0xFFFFFFFFFFFFFFFF, port_index). */
+void shipenv_port_stock(uint64_t seed, uint32_t port_index, uint8_t *fuel, uint8_t *cargo);
+/* kernels launched by this process so far (bench.py's gpu_launches) */
+uint64_t shipenv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHIPENV_H_ */

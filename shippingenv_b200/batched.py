@@ -1,0 +1,217 @@
+"""``BatchedEnvironment``: N independent ShippingEnv ships resident in HBM, advanced by the
+sm_100a kernels behind the C ABI (include/shipenv.h).  PyTorch only owns the memory and the
+stream; every transition is computed by ``libshipenv.so``.
+
+Semantics are the reference's ``Environment`` (shipping/environment.py) per env, plus the
+batched contract of DESIGN.md: a per-env clock (episode << 16 | step), status codes instead of
+exceptions, optional auto-reset, policy actions (-1 = ``sample_action`` until accepted).
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .mapio import derive_grid, passable_of
+
+# reference defaults: utils/constants.py:57-63 and the seed-2024 stock draw
+DEFAULT_PORTS = [[41, 40], [60, 22], [78, 29], [49, 72], [62, 72]]
+DEFAULT_PORT_FUEL = [20, 14, 18, 12, 16]
+DEFAULT_PORT_CARGO = [10, 11, 13, 20, 18]
+
+
+@dataclass
+class StepResult:
+    reward: torch.Tensor                 # float32 [N]
+    done_bits: torch.Tensor              # int32 [ceil(N/32)], bit i%32 of word i//32
+    reset_bits: torch.Tensor
+    error_bits: torch.Tensor
+    reward64: Optional[torch.Tensor] = None
+    status: Optional[torch.Tensor] = None
+    taken: Optional[torch.Tensor] = None
+    obs: Optional[torch.Tensor] = None
+
+
+def unpack_bits(bits, n):
+    """int32 ballot words -> bool [n] (on the words' device)."""
+    shifts = torch.arange(32, device=bits.device, dtype=torch.int32)
+    return ((bits[:, None] >> shifts) & 1).reshape(-1)[:n].bool()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class BatchedEnvironment:
+    def __init__(self, num_envs, passable=None, map_path=None, game_size=(100, 100), ports=None,
+                 port_fuel=None, port_cargo=None, seed=0x5EED, device=None, env_id_base=0,
+                 max_steps=1000, auto_reset=True, consts=None, track_stats=False):
+        if not torch.cuda.is_available():
+            raise nat.ShipEnvError("BatchedEnvironment needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n = int(num_envs)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.env_id_base = int(env_id_base)
+        self.max_steps = int(max_steps)
+        self.auto_reset = bool(auto_reset)
+        if passable is None:
+            if map_path is None:
+                raise ValueError("give either `passable` (uint8 [W,H]) or `map_path`")
+            passable = passable_of(derive_grid(map_path, game_size))
+        self.passable = np.ascontiguousarray(passable, dtype=np.uint8)
+        ports = DEFAULT_PORTS if ports is None else ports
+        P = len(ports)
+        if port_fuel is None or port_cargo is None:
+            if ports == DEFAULT_PORTS and port_fuel is None and port_cargo is None:
+                port_fuel, port_cargo = DEFAULT_PORT_FUEL, DEFAULT_PORT_CARGO
+            else:  # add_port draws, shipping/environment.py:63-64
+                stock = [nat.port_stock(self.seed, k) for k in range(P)]
+                port_fuel = [s[0] for s in stock] if port_fuel is None else port_fuel
+                port_cargo = [s[1] for s in stock] if port_cargo is None else port_cargo
+        W, H = self.passable.shape
+        for x, y in ports:
+            if not (0 <= x < W and 0 <= y < H):
+                raise ValueError("Coordinates not within map")           # shipping/environment.py:60
+        self.ports = [list(map(int, p)) for p in ports]
+        self.port_fuel, self.port_cargo = list(map(int, port_fuel)), list(map(int, port_cargo))
+        self.ctx = nat.Context(self.device.index)
+        self.ctx.set_map(self.passable)
+        self.ctx.set_ports(self.ports, self.port_fuel, self.port_cargo)
+        if consts:
+            self.ctx.set_consts(**consts)
+        self.P = P
+        self.obs_width = 6 + 4 * P
+        self.num_actions = self.ctx.num_actions
+
+        dev, n, nw = self.device, self.n, (self.n + 31) // 32
+        self.ships = torch.zeros((n, 16), dtype=torch.uint8, device=dev)      # shipenv_ship records
+        self.clock = torch.zeros(n, dtype=torch.int32, device=dev)             # u32 bit pattern
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.done_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
+        self.reset_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
+        self.error_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
+        self._reward64 = self._status = self._taken = self._obs = None
+        self.ep_return = self.stats = None
+        if track_stats:
+            self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
+            self.stats = torch.tensor([0, 0, 0, 0, -float("inf"), float("inf")], dtype=torch.float64, device=dev)
+        self._policy = None
+
+    # ---- views of the ship records ------------------------------------------------------
+    @property
+    def x(self): return self.ships[:, 0]
+    @property
+    def y(self): return self.ships[:, 1]
+    @property
+    def origin(self): return self.ships[:, 2]
+    @property
+    def dest(self): return self.ships[:, 3]
+    @property
+    def cargo(self): return self.ships.view(torch.int32)[:, 1]
+    @property
+    def fuel(self): return self.ships.view(torch.float64)[:, 1]
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _buf(self, name, shape, dtype):
+        t = getattr(self, name)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            setattr(self, name, t)
+        return t
+
+    # ---- the reference API, batched -----------------------------------------------------
+    def reset(self, mask_bits=None):
+        """``Environment.reset`` for all envs (or those whose mask bit is set)."""
+        self.ctx.reset(self.ships.data_ptr(), self.clock.data_ptr(), self.seed, self.env_id_base, self.n,
+                       _ptr(mask_bits), self._stream())
+        if self.ep_return is not None and mask_bits is None:
+            self.ep_return.zero_()
+
+    def step(self, actions, want_obs=False, want_status=False, want_taken=False, want_reward64=False,
+             obs_out=None, word0=0):
+        """``Environment.step`` for every env.  ``actions``: int16 [N] flat indices on this device."""
+        if actions.dtype != torch.int16 or actions.device != self.device or actions.numel() != self.n:
+            raise ValueError("actions must be an int16 tensor of shape [num_envs] on the env's device")
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        io = nat.StepIO()
+        io.reward_f32 = self.reward.data_ptr()
+        io.done_bits, io.reset_bits, io.error_bits = (self.done_bits.data_ptr(), self.reset_bits.data_ptr(),
+                                                      self.error_bits.data_ptr())
+        res = StepResult(self.reward, self.done_bits, self.reset_bits, self.error_bits)
+        if want_reward64:
+            res.reward64 = self._buf("_reward64", self.n, torch.float64)
+            io.reward_f64 = res.reward64.data_ptr()
+        if want_status:
+            res.status = self._buf("_status", self.n, torch.uint8)
+            io.status = res.status.data_ptr()
+        if want_taken:
+            res.taken = self._buf("_taken", self.n, torch.int16)
+            io.taken = res.taken.data_ptr()
+        if want_obs or obs_out is not None:
+            res.obs = obs_out if obs_out is not None else self._buf("_obs", (self.n, self.obs_width), torch.float32)
+            if res.obs.dtype != torch.float32 or tuple(res.obs.shape) != (self.n, self.obs_width) \
+                    or not res.obs.is_contiguous():
+                raise ValueError("obs_out must be a contiguous float32 [num_envs, 6+4P] tensor")
+            io.obs = res.obs.data_ptr()
+        if self.ep_return is not None:
+            io.ep_return, io.stats = self.ep_return.data_ptr(), self.stats.data_ptr()
+        flags = nat.F_AUTO_RESET if self.auto_reset else 0
+        self.ctx.step(self.ships.data_ptr(), self.clock.data_ptr(), actions.data_ptr(), io, self.seed,
+                      self.env_id_base, self.n, self.max_steps, flags, word0, self._stream())
+        return res
+
+    def step_policy(self, **kw):
+        """One step of the reference's random policy (``sample_action`` + retry) on every env."""
+        if self._policy is None:
+            self._policy = torch.full((self.n,), nat.ACT_POLICY, dtype=torch.int16, device=self.device)
+        return self.step(self._policy, **kw)
+
+    def observe(self, out=None):
+        """``preprocess_state(env._build_state())`` rows, float32 [N, 6+4P]."""
+        obs = out if out is not None else self._buf("_obs", (self.n, self.obs_width), torch.float32)
+        self.ctx.observe(self.ships.data_ptr(), obs.data_ptr(), self.n, self._stream())
+        return obs
+
+    def sample_action(self, word0=0):
+        """``Environment.sample_action`` per env -> (actions int16 [N], words_used uint8 [N], status uint8 [N])."""
+        a = torch.empty(self.n, dtype=torch.int16, device=self.device)
+        wu = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        st = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        self.ctx.sample_action(self.ships.data_ptr(), self.clock.data_ptr(), a.data_ptr(), wu.data_ptr(),
+                               st.data_ptr(), self.seed, self.env_id_base, self.n, word0, self._stream())
+        return a, wu, st
+
+    def rollout(self, sims, max_steps=100, roots=None, root_id_base=None, want_final=False):
+        """``MCTSAgent._rollout`` x ``sims`` from every root (default: the current ships).
+
+        Returns a dict with ``returns`` float64 [R, sims] and, if asked, ``final`` uint8
+        [R, sims, 16], plus ``steps`` int32 and ``status`` uint8 [R, sims]."""
+        roots = self.ships if roots is None else roots
+        R = roots.shape[0]
+        dev = self.device
+        ret = torch.empty((R, sims), dtype=torch.float64, device=dev)
+        steps = torch.empty((R, sims), dtype=torch.int32, device=dev)
+        status = torch.empty((R, sims), dtype=torch.uint8, device=dev)
+        final = torch.empty((R, sims, 16), dtype=torch.uint8, device=dev) if want_final else None
+        base = self.env_id_base if root_id_base is None else root_id_base
+        self.ctx.rollout(roots.data_ptr(), R, sims, max_steps, ret.data_ptr(), _ptr(final), steps.data_ptr(),
+                         status.data_ptr(), self.seed, base, self._stream())
+        return dict(returns=ret, final=final, steps=steps, status=status)
+
+    # ---- host <-> device state ----------------------------------------------------------
+    def load_state(self, ships_np, clock_np=None):
+        """Overwrite the ship records (numpy structured/uint8 [N,16]) and optionally the clock."""
+        raw = np.ascontiguousarray(ships_np).view(np.uint8).reshape(self.n, 16)
+        self.ships.copy_(torch.from_numpy(raw))
+        if clock_np is not None:
+            self.clock.copy_(torch.from_numpy(np.ascontiguousarray(clock_np, dtype=np.uint32).view(np.int32)))
+
+    def state_numpy(self):
+        """(ships uint8 [N,16], clock uint32 [N]) on the host."""
+        return self.ships.cpu().numpy(), self.clock.cpu().numpy().view(np.uint32)

@@ -1,0 +1,75 @@
+// rng.cuh -- the counter-based word stream every stochastic draw of the environment comes from.
+//
+// The reference draws from CPython's global `random` (shipping/environment.py:3; call sites
+// :63,64,104,157,160,167,177,195,320).  A per-env MT19937 is infeasible on device, so the
+// contract (DESIGN.md "RNG contract") replaces it by Philox4x32-10 cells:
+//     word(i) = Philox4x32-10(ctr = (i >> 2, c1, c2, c3), key = (k0, k1))[i & 3]
+// and defines each `random.*` call the reference makes in terms of words.
+#pragma once
+#include <stdint.h>
+
+namespace shipenv {
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+constexpr uint32_t kRolloutTweak = 0x524F4C4Cu;  // "ROLL"
+constexpr uint32_t kPortTweak = 0x504F5254u;     // "PORT"
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = uint64_t(kPhiloxM0) * c0;
+    const uint64_t p1 = uint64_t(kPhiloxM1) * c2;
+    const uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = uint32_t(p0 >> 32) ^ c3 ^ k1;
+    c1 = uint32_t(p1);
+    c3 = uint32_t(p0);
+    c0 = n0;
+    c2 = n2;
+    k0 += kPhiloxW0;
+    k1 += kPhiloxW1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#ifdef __CUDACC__
+// word * 2^-32 as an exact double without an I2F: 0x41300000:word is 2^20 + word * 2^-32.
+__device__ __forceinline__ double unit_double(uint32_t w) {
+  return __dadd_rn(__hiloint2double(0x41300000, int(w)), -1048576.0);
+}
+
+struct Rng {
+  uint32_t c1, c2, c3, k0, k1;
+  uint32_t i;        // next word of the cell
+  uint32_t blk;      // index of the cached block (i >> 2), ~0u = none
+  uint32_t w[4];
+
+  __device__ __forceinline__ void seek(uint64_t seed, uint32_t tweak, uint32_t cell1, uint64_t id, uint32_t word) {
+    c1 = cell1; c2 = uint32_t(id); c3 = uint32_t(id >> 32);
+    k0 = uint32_t(seed); k1 = uint32_t(seed >> 32) ^ tweak;
+    i = word; blk = ~0u;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    const uint32_t b = i >> 2;
+    if (b != blk) { philox4x32_10(b, c1, c2, c3, k0, k1, w); blk = b; }
+    const uint32_t s = i & 3u;
+    ++i;
+    return s == 0 ? w[0] : s == 1 ? w[1] : s == 2 ? w[2] : w[3];
+  }
+  // random.random()
+  __device__ __forceinline__ double random() { return unit_double(next()); }
+  // random._randbelow(n): one word, (word * n) >> 32
+  __device__ __forceinline__ int below(int n) { return int(__umulhi(next(), uint32_t(n))); }
+  // random.randint(a, b)
+  __device__ __forceinline__ int randint(int a, int b) { return a + below(b - a + 1); }
+  // random.betavariate(2, 2): the median of three uniforms
+  __device__ __forceinline__ double beta22() {
+    const uint32_t a = next(), b = next(), c = next();
+    const uint32_t m = max(min(a, b), min(max(a, b), c));
+    return unit_double(m);
+  }
+};
+#endif
+
+}  // namespace shipenv

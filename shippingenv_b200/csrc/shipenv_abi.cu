@@ -1,0 +1,365 @@
+// shipenv_abi.cu -- the C ABI of include/shipenv.h: context, world upload, kernel launches.
+// Host logic only; all arithmetic of the hot path is in kernels.cuh / transition.cuh.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace shipenv;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess) return fail(SHIPENV_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+// Restores the caller's current device on scope exit (torch tracks it through the runtime).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+const shipenv_consts kDefaultConsts = {
+    /*cargo0*/ 0, /*capacity*/ 50, /*fuel0*/ 200.0,
+    /*r_deliver*/ 2.0, /*r_arrive*/ 10.0, /*r_closer*/ 2.0, /*r_take_fuel*/ 0.05, /*r_take_cargo*/ 0.05,
+    /*p_no_fuel*/ -10.0, /*p_ground*/ -5.0, /*p_water*/ -1.0, /*p_loss*/ -3.0, /*p_farther*/ -2.0,
+    /*p_use_fuel*/ -0.0001};
+
+}  // namespace
+
+struct shipenv_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  // host mirror of the world
+  int W = 0, H = 0, P = -1;
+  std::vector<uint8_t> passable;
+  uint8_t px[kMaxPorts], py[kMaxPorts], pfuel[kMaxPorts], pcargo[kMaxPorts];
+  shipenv_consts consts = kDefaultConsts;
+  // device blob
+  void* d_world = nullptr;
+  std::vector<unsigned char> h_world;
+  uint32_t world_bytes = 0;
+  bool dirty = true;
+  // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
+  struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
+  Occ occ_step, occ_step_obs, occ_reset, occ_observe, occ_sample, occ_rollout;
+};
+
+namespace {
+
+// Build the blob from the host mirror.  The reward table is accumulated exactly as
+// _move_ship does (shipping/environment.py:278-315): r = 0; (+no_fuel); (+ground | +use_fuel,
+// +water); (+closer | +farther) -- one rounded fp64 add at a time.
+int build_world(shipenv_ctx* c) {
+  if (c->W <= 0) return fail(SHIPENV_E_STATE, "no map set (shipenv_set_map)");
+  if (c->P < 0) return fail(SHIPENV_E_STATE, "no port table set (shipenv_set_ports)");
+  const int wpr = (c->H + 31) / 32;
+  const size_t n_words = size_t(c->W) * wpr;
+  const size_t bytes = (sizeof(WorldHdr) + n_words * 4 + 15) & ~size_t(15);
+  c->h_world.assign(bytes, 0);
+  WorldHdr* h = new (c->h_world.data()) WorldHdr();
+  uint32_t* bits = reinterpret_cast<uint32_t*>(c->h_world.data() + sizeof(WorldHdr));
+  const shipenv_consts& k = c->consts;
+  h->W = c->W; h->H = c->H; h->P = c->P; h->wpr = wpr;
+  h->cargo0 = k.cargo0; h->capacity = k.capacity;
+  h->n_bit_words = int32_t(n_words); h->total_bytes = int32_t(bytes);
+  h->fuel0 = k.fuel0;
+  h->r_take_fuel = k.r_take_fuel; h->r_take_cargo = k.r_take_cargo;
+  h->r_deliver = k.r_deliver; h->r_arrive = k.r_arrive; h->p_loss = k.p_loss;
+  for (int idx = 0; idx < 8; ++idx) {
+    volatile double r = 0.0;  // volatile: one rounded add per statement, no contraction
+    if (idx & 4) r = r + k.p_no_fuel;
+    if (idx & 2) { r = r + k.p_ground; }
+    else { r = r + k.p_use_fuel; r = r + k.p_water; }
+    if (idx & 1) r = r + k.r_closer; else r = r + k.p_farther;
+    h->move_reward[idx] = r;
+  }
+  for (int p = 0; p < c->P; ++p) {
+    h->port[p] = uint32_t(c->px[p]) | (uint32_t(c->py[p]) << 8) | (uint32_t(c->pfuel[p]) << 16) |
+                 (uint32_t(c->pcargo[p]) << 24);
+    h->obs_tail[4 * p + 0] = float(c->px[p]); h->obs_tail[4 * p + 1] = float(c->py[p]);
+    h->obs_tail[4 * p + 2] = float(c->pfuel[p]); h->obs_tail[4 * p + 3] = float(c->pcargo[p]);
+  }
+  for (int cg = 0; cg < k.capacity && cg < kMaxCap; ++cg) {
+    volatile double q = double(cg) / double(k.capacity);  // normalize(), shipping/util.py:6-8
+    h->loss_thr[cg] = uint32_t(q * 4294967296.0);          // exact scaling, then floor
+  }
+  for (int x = 0; x < c->W; ++x)
+    for (int y = 0; y < c->H; ++y)
+      if (c->passable[size_t(x) * c->H + y]) bits[size_t(x) * wpr + (y >> 5)] |= 1u << (y & 31);
+  // a port cell is passable whatever the map says (add_port stamps Entity.PORT, :65)
+  for (int p = 0; p < c->P; ++p)
+    if (c->px[p] < c->W && c->py[p] < c->H) bits[size_t(c->px[p]) * wpr + (c->py[p] >> 5)] |= 1u << (c->py[p] & 31);
+  c->world_bytes = uint32_t(bytes);
+  return 0;
+}
+
+int sync_world(shipenv_ctx* c, cudaStream_t stream) {
+  if (!c->dirty) return 0;
+  if (int rc = build_world(c)) return rc;
+  // pageable source: the runtime stages the bytes before returning, so h_world may change later
+  CUDA_TRY(cudaMemcpyAsync(c->d_world, c->h_world.data(), c->world_bytes, cudaMemcpyHostToDevice, stream));
+  c->dirty = false;
+  return 0;
+}
+
+template <class Kernel>
+int grid_for(shipenv_ctx* c, Kernel kernel, shipenv_ctx::Occ& occ, int threads, size_t smem, int64_t tiles, int* grid) {
+  if (occ.smem != smem) {
+    if (smem > 48 * 1024) {
+      if (smem > size_t(c->max_smem_optin)) return fail(SHIPENV_E_ARG, "needs %zu B of shared memory per CTA", smem);
+      CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    }
+    int blocks = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, threads, smem));
+    if (blocks < 1) return fail(SHIPENV_E_CUDA, "kernel does not fit an SM");
+    occ.smem = smem;
+    occ.blocks = blocks;
+  }
+  const int64_t resident = int64_t(c->sm_count) * occ.blocks;  // persistent: one wave of CTAs
+  *grid = int(tiles < resident ? tiles : resident);
+  if (*grid < 1) *grid = 1;
+  return 0;
+}
+
+int check_ctx(shipenv_ctx* c) {
+  if (!c) return fail(SHIPENV_E_ARG, "null context");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int shipenv_abi_version(void) { return SHIPENV_ABI_VERSION; }
+const char* shipenv_last_error(void) { return g_err; }
+uint64_t shipenv_launch_count(void) { return g_launches.load(); }
+
+void shipenv_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+
+void shipenv_port_stock(uint64_t seed, uint32_t port_index, uint8_t* fuel, uint8_t* cargo) {
+  uint32_t w[4];
+  philox4x32_10(0u, port_index, 0xFFFFFFFFu, 0xFFFFFFFFu, uint32_t(seed), uint32_t(seed >> 32) ^ kPortTweak, w);
+  // random.randint(5, 20) twice: fuel then cargo (shipping/environment.py:63-64)
+  *fuel = uint8_t(5 + ((uint64_t(w[0]) * 16u) >> 32));
+  *cargo = uint8_t(5 + ((uint64_t(w[1]) * 16u) >> 32));
+}
+
+int shipenv_ctx_create(int device, shipenv_ctx** out) {
+  if (!out) return fail(SHIPENV_E_ARG, "out is null");
+  *out = nullptr;
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(SHIPENV_E_ARG, "device %d out of range (%d visible)", device, count);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(SHIPENV_E_CUDA, "cannot select device %d", device);
+  int major = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return fail(SHIPENV_E_CUDA, "device %d is sm_%dx; this library is built for sm_100a only", device, major);
+  shipenv_ctx* c = new (std::nothrow) shipenv_ctx();
+  if (!c) return fail(SHIPENV_E_ARG, "out of host memory");
+  c->device = device;
+  CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  cudaError_t e = cudaMalloc(&c->d_world, kMaxWorldBytes);
+  if (e != cudaSuccess) { delete c; return fail(SHIPENV_E_CUDA, "cudaMalloc(world): %s", cudaGetErrorString(e)); }
+  *out = c;
+  return 0;
+}
+
+int shipenv_ctx_destroy(shipenv_ctx* c) {
+  if (!c) return 0;
+  {
+    DeviceGuard guard(c->device);
+    if (c->d_world) cudaFree(c->d_world);
+  }
+  delete c;
+  return 0;
+}
+
+int shipenv_set_map(shipenv_ctx* c, const uint8_t* passable, int W, int H) {
+  if (int rc = check_ctx(c)) return rc;
+  if (!passable) return fail(SHIPENV_E_ARG, "passable is null");
+  if (W < 1 || H < 1 || W > kMaxDim || H > kMaxDim) return fail(SHIPENV_E_ARG, "map %dx%d outside 1..%d", W, H, kMaxDim);
+  c->W = W; c->H = H;
+  c->passable.assign(passable, passable + size_t(W) * H);
+  c->dirty = true;
+  return 0;
+}
+
+int shipenv_set_ports(shipenv_ctx* c, const uint8_t* px, const uint8_t* py, const uint8_t* pfuel,
+                      const uint8_t* pcargo, int P) {
+  if (int rc = check_ctx(c)) return rc;
+  if (P < 0 || P > kMaxPorts) return fail(SHIPENV_E_ARG, "P=%d outside 0..%d", P, kMaxPorts);
+  if (P > 0 && (!px || !py || !pfuel || !pcargo)) return fail(SHIPENV_E_ARG, "null port table");
+  for (int p = 0; p < P; ++p) { c->px[p] = px[p]; c->py[p] = py[p]; c->pfuel[p] = pfuel[p]; c->pcargo[p] = pcargo[p]; }
+  c->P = P;
+  c->dirty = true;
+  return 0;
+}
+
+int shipenv_set_consts(shipenv_ctx* c, const shipenv_consts* k) {
+  if (int rc = check_ctx(c)) return rc;
+  const shipenv_consts v = k ? *k : kDefaultConsts;
+  if (v.capacity < 1 || v.capacity > SHIPENV_MAX_CAPACITY) return fail(SHIPENV_E_ARG, "capacity %d outside 1..%d", v.capacity, SHIPENV_MAX_CAPACITY);
+  c->consts = v;
+  c->dirty = true;
+  return 0;
+}
+
+int shipenv_get_consts(shipenv_ctx* c, shipenv_consts* out) {
+  if (int rc = check_ctx(c)) return rc;
+  if (!out) return fail(SHIPENV_E_ARG, "out is null");
+  *out = c->consts;
+  return 0;
+}
+
+int shipenv_obs_width(shipenv_ctx* c) { return (c && c->P >= 0) ? 6 + 4 * c->P : SHIPENV_E_STATE; }
+int shipenv_num_actions(shipenv_ctx* c) {
+  return (c && c->P >= 0) ? 4 + c->P + SHIPENV_N_CARGO_ACTIONS + SHIPENV_N_FUEL_ACTIONS : SHIPENV_E_STATE;
+}
+
+int shipenv_reset(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, uint64_t seed, uint64_t env_id_base,
+                  int64_t n, const uint32_t* mask_bits, void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (n < 0 || (n > 0 && (!ships || !clock))) return fail(SHIPENV_E_ARG, "reset: null buffer or negative n");
+  if (n == 0) return 0;
+  if (c->P < 2) return fail(SHIPENV_E_STATE, "reset needs at least 2 ports (the reference loops forever with 1, raises with 0)");
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  ResetArgs a{c->d_world, c->world_bytes, reinterpret_cast<uint4*>(ships), clock, mask_bits, seed, env_id_base, n};
+  const size_t smem = c->world_bytes;
+  int grid = 0;
+  if (int rc = grid_for(c, reset_kernel, c->occ_reset, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
+  reset_kernel<<<grid, kThreads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* actions,
+                 const shipenv_step_io* io, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
+                 uint32_t flags, uint32_t word0, void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (n < 0 || (n > 0 && (!ships || !clock || !actions))) return fail(SHIPENV_E_ARG, "step: null buffer or negative n");
+  if (max_steps < 0 || max_steps > 65535) return fail(SHIPENV_E_ARG, "max_steps %d outside 0..65535", max_steps);
+  if (n == 0) return 0;
+  if ((flags & SHIPENV_F_AUTO_RESET) && c->P < 2) return fail(SHIPENV_E_STATE, "auto-reset needs at least 2 ports");
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  StepArgs a{};
+  a.world = c->d_world; a.world_bytes = c->world_bytes;
+  a.ships = reinterpret_cast<uint4*>(ships); a.clock = clock; a.actions = actions;
+  if (io) a.io = *io; else memset(&a.io, 0, sizeof(a.io));
+  a.seed = seed; a.env_id_base = env_id_base; a.n = n; a.max_steps = max_steps; a.flags = flags; a.word0 = word0;
+  a.obs_width = 6 + 4 * c->P;
+  const int64_t tiles = (n + kThreads - 1) / kThreads;
+  int grid = 0;
+  if (a.io.obs) {
+    if (reinterpret_cast<uintptr_t>(a.io.obs) & 15u) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
+    const size_t base = (size_t(c->world_bytes) + 127) & ~size_t(127);
+    const size_t tile_bytes = size_t(kThreads) * a.obs_width * 4;
+    a.obs_bufs = (base + 2 * tile_bytes <= 64 * 1024) ? 2 : 1;
+    const size_t smem = base + a.obs_bufs * tile_bytes;
+    if (int rc = grid_for(c, step_kernel<true>, c->occ_step_obs, kThreads, smem, tiles, &grid)) return rc;
+    step_kernel<true><<<grid, kThreads, smem, stream>>>(a);
+  } else {
+    const size_t smem = c->world_bytes;
+    if (int rc = grid_for(c, step_kernel<false>, c->occ_step, kThreads, smem, tiles, &grid)) return rc;
+    step_kernel<false><<<grid, kThreads, smem, stream>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int shipenv_sample_action(shipenv_ctx* c, const shipenv_ship* ships, const uint32_t* clock, int16_t* actions_out,
+                          uint8_t* words_used, uint8_t* status, uint64_t seed, uint64_t env_id_base, int64_t n,
+                          uint32_t word0, void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (n < 0 || (n > 0 && (!ships || !clock || !actions_out))) return fail(SHIPENV_E_ARG, "sample_action: null buffer or negative n");
+  if (n == 0) return 0;
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  SampleArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(ships), clock, actions_out, words_used,
+               status, seed, env_id_base, n, word0};
+  const size_t smem = c->world_bytes;
+  int grid = 0;
+  if (int rc = grid_for(c, sample_kernel, c->occ_sample, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
+  sample_kernel<<<grid, kThreads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int shipenv_observe(shipenv_ctx* c, const shipenv_ship* ships, float* obs, int64_t n, void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (n < 0 || (n > 0 && (!ships || !obs))) return fail(SHIPENV_E_ARG, "observe: null buffer or negative n");
+  if (reinterpret_cast<uintptr_t>(obs) & 15u) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
+  if (n == 0) return 0;
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  ObserveArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(ships), obs, n, 6 + 4 * c->P};
+  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + size_t(kThreads) * a.obs_width * 4;
+  int grid = 0;
+  if (int rc = grid_for(c, observe_kernel, c->occ_observe, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
+  observe_kernel<<<grid, kThreads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int shipenv_rollout(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S, int L, double* returns,
+                    shipenv_ship* final, int32_t* steps, uint8_t* status, uint64_t seed, uint64_t root_id_base,
+                    void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (R < 0 || S < 0 || L < 0) return fail(SHIPENV_E_ARG, "rollout: negative size");
+  if (R * int64_t(S) > 0 && (!roots || !returns)) return fail(SHIPENV_E_ARG, "rollout: null buffer");
+  if (R == 0 || S == 0) return 0;
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  RolloutArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, returns,
+                reinterpret_cast<uint4*>(final), steps, status, seed, root_id_base};
+  const size_t smem = c->world_bytes;
+  const int64_t tiles = (R * int64_t(S) + kRolloutThreads - 1) / kRolloutThreads;
+  int grid = 0;
+  if (int rc = grid_for(c, rollout_kernel, c->occ_rollout, kRolloutThreads, smem, tiles, &grid)) return rc;
+  rollout_kernel<<<grid, kRolloutThreads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+}  // extern "C"

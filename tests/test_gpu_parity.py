@@ -1,0 +1,199 @@
+"""GPU: the CUDA path, called through the C ABI, against the reference-generated fixtures and
+against the CPU oracle on seeded inputs.  Bit-exact for positions, ports, cargo, fuel (f64 bits),
+done/reset/status, clock and the f64 reward; the f32 reward is the f64 one rounded once."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import lib as orc
+from tracecheck import TRACES, CudaStepper, replay
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.mark.parametrize("name", TRACES)
+def test_cuda_replays_reference_trace(torch_cuda, name):
+    z = golden(name)
+    assert replay(z, CudaStepper(z)) > 0
+
+
+def test_cuda_reset_matches_reference(torch_cuda):
+    from shippingenv_b200 import BatchedEnvironment
+    z = golden("g1_moves")
+    n = z["init_cargo"].shape[0]
+    env = BatchedEnvironment(n, passable=z["passable"], seed=int(z["seed"]), device="cuda:0")
+    env.reset()
+    ships, clock = env.state_numpy()
+    want = orc.ships_from(z["init_pos"], z["init_cargo"], z["init_fuel"])
+    assert ships.tobytes() == want.tobytes()
+    assert (clock == 65536).all()
+
+
+def test_cuda_masked_reset(torch_cuda):
+    torch = torch_cuda
+    from shippingenv_b200 import BatchedEnvironment
+    z = golden("default_map")
+    n = 100
+    env = BatchedEnvironment(n, passable=z["passable"], device="cuda:0")
+    env.reset()
+    before, clk0 = env.state_numpy()
+    env.step_policy()
+    mid, clk1 = env.state_numpy()
+    mask = np.zeros(4, np.uint32)
+    chosen = [0, 5, 31, 32, 64, 99]
+    for i in chosen:
+        mask[i >> 5] |= np.uint32(1 << (i & 31))
+    env.reset(torch.from_numpy(mask.view(np.int32)).to(env.device))
+    after, clk2 = env.state_numpy()
+    o = orc.Oracle(z["passable"], env.ports, env.port_fuel, env.port_cargo)
+    ships, clock = mid.view(orc.SHIP_DTYPE).reshape(-1).copy(), clk1.copy()
+    m8 = np.zeros(n, np.uint8); m8[chosen] = 1
+    o.reset(ships, clock, env.seed, 0, m8)
+    assert after.tobytes() == ships.tobytes() and (clk2 == clock).all()
+    assert (clk2[chosen] == 2 << 16).all() and (np.delete(clk2, chosen) == (1 << 16) + 1).all()
+
+
+@pytest.mark.parametrize("n,policy_every", [(1, 2), (33, 3), (4096, 4), (50_000, 0)])
+def test_cuda_vs_oracle_seeded(torch_cuda, default_map, n, policy_every):
+    """Config 2 of BASELINE.json (4,096 envs, default map and ports, random actions, auto-reset),
+    and ragged sizes around it, against the oracle for 256 steps."""
+    torch = torch_cuda
+    from shippingenv_b200 import BatchedEnvironment, unpack_bits
+    seed, max_steps = 0x5EED, 1000 if n == 4096 else 150
+    env = BatchedEnvironment(n, passable=default_map["passable"], seed=seed, device="cuda:0",
+                             max_steps=max_steps, auto_reset=True)
+    o = orc.Oracle(default_map["passable"], env.ports, env.port_fuel, env.port_cargo)
+    ships, clock = np.zeros(n, orc.SHIP_DTYPE), np.zeros(n, np.uint32)
+    env.reset(); o.reset(ships, clock, seed)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    T = 256 if n <= 4096 else 64
+    n_done = 0
+    for t in range(T):
+        a = torch.randint(0, 4, (n,), generator=gen, device="cuda", dtype=torch.int16)
+        if policy_every and t % policy_every == 0:
+            a.fill_(-1)
+        r = env.step(a, want_status=True, want_reward64=True, want_taken=True)
+        ref = o.step(ships, clock, a.cpu().numpy(), seed, 0, max_steps, True)
+        g_ships, g_clock = env.state_numpy()
+        assert g_ships.tobytes() == ships.tobytes(), f"ships differ at step {t}"
+        assert (g_clock == clock).all()
+        assert (r.reward64.cpu().numpy().view(np.uint64) == ref["reward"].view(np.uint64)).all()
+        assert (r.reward.cpu().numpy() == ref["reward"].astype(np.float32)).all()
+        assert (r.status.cpu().numpy() == ref["status"]).all()
+        assert (unpack_bits(r.done_bits, n).cpu().numpy() == ref["done"].astype(bool)).all()
+        assert (unpack_bits(r.reset_bits, n).cpu().numpy() == ref["reset"].astype(bool)).all()
+        ok = ref["status"] == 0
+        assert (r.taken.cpu().numpy()[ok] == ref["taken"][ok]).all()
+        n_done += int(ref["done"].sum())
+    if n >= 4096:
+        assert n_done > 0
+
+
+def test_cuda_observation(torch_cuda):
+    """Fused observation epilogue and the stand-alone observe kernel == preprocess_state rows."""
+    torch = torch_cuda
+    from shippingenv_b200 import BatchedEnvironment
+    z = golden("g2_policy")
+    n = 64
+    env = BatchedEnvironment(n, passable=z["passable"], seed=int(z["seed"]), device="cuda:0")
+    env.load_state(orc.ships_from(z["pos"][-1], z["cargo"][-1], z["fuel"][-1]), z["clock"][-1])
+    obs = env.observe().cpu().numpy()
+    assert (obs.view(np.uint32) == z["obs"].view(np.uint32)).all()
+    # fused: step with observation output for ragged sizes, compared with the oracle's rows
+    for n in (1, 7, 255, 256, 257, 1000, 5001):
+        env = BatchedEnvironment(n, passable=z["passable"], seed=7, device="cuda:0", max_steps=40)
+        o = orc.Oracle(z["passable"], env.ports, env.port_fuel, env.port_cargo)
+        ships, clock = np.zeros(n, orc.SHIP_DTYPE), np.zeros(n, np.uint32)
+        env.reset(); o.reset(ships, clock, 7)
+        for t in range(50):
+            r = env.step_policy(want_obs=True)
+            o.step(ships, clock, np.full(n, -1, np.int16), 7, 0, 40, True)
+            want = o.observe(ships)
+            got = r.obs.cpu().numpy()
+            assert (got.view(np.uint32) == want.view(np.uint32)).all(), f"n={n} step {t}"
+        assert env.state_numpy()[0].tobytes() == ships.tobytes()
+        assert (env.observe().cpu().numpy() == want).all()
+
+
+@pytest.mark.parametrize("L", [100, 25])
+def test_cuda_rollout_matches_reference_rollout(torch_cuda, L):
+    torch = torch_cuda
+    from shippingenv_b200 import BatchedEnvironment
+    z = golden("g8_rollouts")
+    roots = orc.ships_from(z["root_pos"], z["root_cargo"], z["root_fuel"])
+    R, S = z[f"ret_L{L}"].shape
+    env = BatchedEnvironment(R, passable=z["passable"], seed=int(z["seed"]), device="cuda:0")
+    env.load_state(roots)
+    out = env.rollout(S, L, root_id_base=int(z["root_id_base"]), want_final=True)
+    assert (out["status"].cpu().numpy() == 0).all()
+    assert (out["returns"].cpu().numpy().view(np.uint64) == z[f"ret_L{L}"]).all()
+    fin = out["final"].cpu().numpy().view(orc.SHIP_DTYPE).reshape(R, S)
+    assert (np.stack([fin["x"], fin["y"], fin["origin"], fin["dest"]], -1) == z[f"fin_pos_L{L}"]).all()
+    assert (fin["cargo"] == z[f"fin_cargo_L{L}"]).all()
+    assert (fin["fuel"].view(np.uint64) == z[f"fin_fuel_L{L}"]).all()
+
+
+def test_cuda_rollout_vs_oracle_large(torch_cuda, default_map):
+    """Config 4 shape at a size the oracle finishes in seconds: 2,048 roots x 50 sims x 100 steps."""
+    from shippingenv_b200 import BatchedEnvironment
+    R, S, L, seed = 2048, 50, 100, 99
+    env = BatchedEnvironment(R, passable=default_map["passable"], seed=seed, device="cuda:0", auto_reset=False)
+    env.reset()
+    for _ in range(10):
+        env.step_policy()
+    roots, _ = env.state_numpy()
+    o = orc.Oracle(default_map["passable"], env.ports, env.port_fuel, env.port_cargo)
+    want, fin, steps, status = o.rollout(roots.view(orc.SHIP_DTYPE).reshape(-1), S, L, seed)
+    out = env.rollout(S, L, want_final=True)
+    assert (out["returns"].cpu().numpy().view(np.uint64) == want.view(np.uint64)).all()
+    assert out["final"].cpu().numpy().tobytes() == fin.tobytes()
+    assert (out["steps"].cpu().numpy() == steps).all()
+
+
+def test_cuda_sample_action(torch_cuda, default_map):
+    from shippingenv_b200 import BatchedEnvironment
+    n, seed = 3000, 5
+    env = BatchedEnvironment(n, passable=default_map["passable"], seed=seed, device="cuda:0", auto_reset=False)
+    env.reset()
+    o = orc.Oracle(default_map["passable"], env.ports, env.port_fuel, env.port_cargo)
+    for t in range(20):
+        a, words, st = env.sample_action()
+        # sample_action() then step(a) with word0 = words consumed == one policy step when accepted
+        ships, clock = env.state_numpy()
+        ships = ships.view(orc.SHIP_DTYPE).reshape(-1).copy(); clock = clock.copy()
+        ref = o.step(ships, clock, np.full(n, -1, np.int16), seed, 0, 0, False)
+        assert (st.cpu().numpy() == 0).all() and (words.cpu().numpy() == 1).all()
+        r = env.step(a, want_status=True, word0=1)
+        acc = r.status.cpu().numpy() == 0
+        # where the first draw was accepted, the policy step took the same action
+        assert (a.cpu().numpy()[acc] == ref["taken"][acc]).mean() > 0.99
+        same = acc & (a.cpu().numpy() == ref["taken"])
+        got, _ = env.state_numpy()
+        assert (got.view(orc.SHIP_DTYPE).reshape(-1)[same] == ships[same]).all()
+
+
+def test_cuda_consts_can_vary(torch_cuda, default_map):
+    """The constants struct reaches the kernel: different rewards / fuel / capacity, still oracle-exact."""
+    torch = torch_cuda
+    from shippingenv_b200 import BatchedEnvironment
+    consts = dict(fuel0=37.5, cargo0=3, capacity=20, r_deliver=1.25, r_arrive=7.0, r_closer=0.3,
+                  p_no_fuel=-4.0, p_ground=-0.7, p_water=-0.11, p_loss=-1.3, p_farther=-0.9, p_use_fuel=-0.003,
+                  r_take_fuel=0.4, r_take_cargo=0.6)
+    n, seed = 2000, 11
+    env = BatchedEnvironment(n, passable=default_map["passable"], seed=seed, device="cuda:0", max_steps=90,
+                             consts=consts)
+    o = orc.Oracle(default_map["passable"], env.ports, env.port_fuel, env.port_cargo, **consts)
+    ships, clock = np.zeros(n, orc.SHIP_DTYPE), np.zeros(n, np.uint32)
+    env.reset(); o.reset(ships, clock, seed)
+    for t in range(200):
+        r = env.step_policy(want_reward64=True)
+        ref = o.step(ships, clock, np.full(n, -1, np.int16), seed, 0, 90, True)
+        assert env.state_numpy()[0].tobytes() == ships.tobytes(), t
+        assert (r.reward64.cpu().numpy().view(np.uint64) == ref["reward"].view(np.uint64)).all(), t
