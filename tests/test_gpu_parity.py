@@ -92,8 +92,8 @@ def test_cuda_vs_oracle_seeded(torch_cuda, default_map, n, policy_every):
         ok = ref["status"] == 0
         assert (r.taken.cpu().numpy()[ok] == ref["taken"][ok]).all()
         n_done += int(ref["done"].sum())
-    if n >= 4096:
-        assert n_done > 0
+    if n == 4096:
+        assert n_done > 0      # some ships run out of fuel within 256 steps
 
 
 def test_cuda_observation(torch_cuda):
