@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 2,097,152 envs
-per GPU (16M over 8), default map, 5 default ports, uniform random move actions, auto-reset on
+per launch per GPU (16M over 8), default map, 5 default ports, uniform random move actions, auto-reset on
 done or after 1,000 steps, Philox seed 0x5EED, global env ids rank * 2^21 + i (weak scaling, no
 collective on the step path).  One "step" = one shipenv_step launch over every env of the rank.
 
@@ -29,6 +29,7 @@ ENVS_PER_GPU = 1 << 21
 SEED = 0x5EED
 MAX_STEPS = 1000
 BYTES_PER_STEP = 46          # 16+4+2 read, 16+4+4 written, + 3 ballot bits
+GROUPS = 4                   # env groups per GPU, stepped round-robin (working set > L2)
 ACTION_POOL = 32             # distinct pre-generated action vectors, cycled
 FLUSH_BYTES = 256 << 20      # > 126 MB L2
 METRIC = "env-steps/sec (whole box)"
@@ -191,8 +192,9 @@ def workload_config(gpus):
     return {"workload": f"{ENVS_PER_GPU} envs/GPU x {gpus} GPU(s) (BASELINE configs[2]: 16M envs over 8 GPUs), "
                         "default 100x100 map, 5 default ports, uniform random N/E/S/W actions (int16, pre-generated on "
                         "device), auto-reset on done or 1000 steps, Philox seed 0x5EED",
-            "envs_per_gpu": ENVS_PER_GPU, "max_steps": MAX_STEPS,
-            "l2": "flushed between timed steps (256 MiB fill, outside the per-step event pairs)",
+            "envs_per_launch": ENVS_PER_GPU, "env_groups_per_gpu": GROUPS, "max_steps": MAX_STEPS,
+            "l2": "inputs larger than L2: 4 env groups of 2,097,152 envs per GPU stepped round-robin (216 MB working "
+                  "set vs 126 MB L2), K launches back to back between two CUDA events",
             "bytes_per_env_step": BYTES_PER_STEP}
 
 
@@ -217,12 +219,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.envs
-    env = BatchedEnvironment(n, passable=world(), seed=SEED, device=dev, env_id_base=rank * n,
-                             max_steps=MAX_STEPS, auto_reset=True)
-    env.reset()
+    G = args.groups
+    # G independent env groups per GPU, stepped round-robin: one launch touches 46 B x n = 96 MB and the
+    # next G-1 launches stream 3 x 96 MB through the 126 MB L2 before the group comes round again, so
+    # every timed launch reads its inputs from HBM ("inputs larger than L2").
+    envs = [BatchedEnvironment(n, passable=world(), seed=SEED, device=dev, env_id_base=(rank * G + g) * n,
+                               max_steps=MAX_STEPS, auto_reset=True) for g in range(G)]
+    for e in envs:
+        e.reset()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = [torch.randint(0, 4, (n,), generator=gen, device=dev, dtype=torch.int16) for _ in range(ACTION_POOL)]
-    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -230,67 +236,78 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident: per-step CUDA events on the launching stream, L2 flushed in between ----
+    # ---- device-resident: K back-to-back launches between two CUDA events on the launching stream ----
     for t in range(W):
-        env.step(pool[t % ACTION_POOL])
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        envs[t % G].step(pool[t % ACTION_POOL])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = launch_count()
     with ClockSampler(local) as clocks:
+        e0.record()
         for t in range(K):
-            flush.fill_(t & 255)
-            starts[t].record()
-            env.step(pool[t % ACTION_POOL])
-            stops[t].record()
+            envs[t % G].step(pool[t % ACTION_POOL])
+        e1.record()
         barrier()
     launches = launch_count() - launches0
-    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-    total_ms = sum(per_step_ms)
-    err = int(env.error_bits.ne(0).sum().item())
+    total_ms = e0.elapsed_time(e1)
+    err = int(sum(int(e.error_bits.ne(0).sum().item()) for e in envs))
 
-    # ---- L2-warm variant: K back-to-back launches between two events (reported separately) ----
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- single group, L2 flushed by a 256 MiB fill between steps, one event pair per step (reported separately) ----
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    Kf = min(K, 256)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
     barrier()
-    e0.record()
-    for t in range(K):
-        env.step(pool[t % ACTION_POOL])
-    e1.record()
+    for t in range(Kf):
+        flush.fill_(t & 255)
+        starts[t].record()
+        envs[0].step(pool[t % ACTION_POOL])
+        stops[t].record()
     barrier()
-    warm_ms = e0.elapsed_time(e1)
+    flushed_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops)) * K / Kf
+    del flush
 
-    # ---- end to end: actions from pinned host memory, reward + masks back to pinned host ----
-    h_act = [torch.randint(0, 4, (n,), dtype=torch.int16).pin_memory() for _ in range(4)]
-    d_act = torch.empty(n, dtype=torch.int16, device=dev)
+    # ---- end to end: actions from pinned host memory, reward + masks back to pinned host memory ----
+    # one stream per group: copies of one group overlap the kernel of another
     nw = (n + 31) // 32
-    h_reward = torch.empty(n, dtype=torch.float32).pin_memory()
-    h_done = torch.empty(nw, dtype=torch.int32).pin_memory()
-    h_reset = torch.empty(nw, dtype=torch.int32).pin_memory()
-    Ke = max(8, min(K, 64))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
+    h_act = [torch.randint(0, 4, (n,), dtype=torch.int16).pin_memory() for _ in range(G)]
+    d_act = [torch.empty(n, dtype=torch.int16, device=dev) for _ in range(G)]
+    h_reward = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(G)]
+    h_done = [torch.empty(nw, dtype=torch.int32).pin_memory() for _ in range(G)]
+    h_reset = [torch.empty(nw, dtype=torch.int32).pin_memory() for _ in range(G)]
+    Ke = max(8, min(K, 128))
 
     def e2e_step(t):
-        d_act.copy_(h_act[t % 4], non_blocking=True)
-        r = env.step(d_act)
-        h_reward.copy_(r.reward, non_blocking=True)
-        h_done.copy_(r.done_bits, non_blocking=True)
-        h_reset.copy_(r.reset_bits, non_blocking=True)
+        g = t % G
+        with torch.cuda.stream(streams[g]):
+            d_act[g].copy_(h_act[g], non_blocking=True)
+            r = envs[g].step(d_act[g])
+            h_reward[g].copy_(r.reward, non_blocking=True)
+            h_done[g].copy_(r.done_bits, non_blocking=True)
+            h_reset[g].copy_(r.reset_bits, non_blocking=True)
 
-    for t in range(3):
+    for t in range(2 * G):
         e2e_step(t)
     barrier()
-    e0.record()
+    t0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+    t0.record()                                  # on the current stream; the group streams wait for it
+    for st in streams:
+        st.wait_event(t0)
     for t in range(Ke):
         e2e_step(t)
-    e1.record()
+    for g, st in enumerate(streams):
+        ends[g].record(st)
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    checksum = float(h_reward.sum())
+    e2e_ms = max(t0.elapsed_time(e) for e in ends)
+    checksum = float(sum(float(h.sum()) for h in h_reward))
 
     # ---- max over ranks ----
-    times = torch.tensor([total_ms, warm_ms, e2e_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([total_ms, flushed_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, warm_ms, e2e_ms = times.tolist()
+    total_ms, flushed_ms, e2e_ms = times.tolist()
 
     if rank == 0:
         n_total = n * world_size
@@ -310,15 +327,16 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world_size, "steps": K,
             "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world_size),
-            "value_l2_warm": n_total * K / (warm_ms * 1e-3),
+            "value_l2_flushed_per_step_events": n_total * K / (flushed_ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "shipenv::step_kernel<false>",
+                         "kernel": "shipenv::step_fast_kernel",
                          "algorithmic_bytes_per_launch": n * BYTES_PER_STEP},
             "e2e": {"value": n_total * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n + 8 * nw, "steps": Ke,
-                    "what": "shipenv_step via BatchedEnvironment.step: int16 actions from pinned host memory, "
-                            "f32 reward + done/reset masks to pinned host memory, one stream"},
+                    "what": "shipenv_step via BatchedEnvironment.step: int16 actions from pinned host memory, f32 reward "
+                            "+ done/reset masks to pinned host memory; one stream per env group so that copies "
+                            "overlap kernels"},
             "gpu_launches": launches, "clocks": clocks.summary(),
             "rejected_actions_last_step": err, "reward_checksum": checksum,
         }
@@ -342,7 +360,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2048)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per launch")
+    ap.add_argument("--groups", type=int, default=GROUPS, help="env groups per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libshipenv.so")
+LIB_PATH = os.environ.get("SHIPENV_LIB") or os.path.join(HERE, "libshipenv.so")   # SHIPENV_LIB: tuning builds only
 
 MAX_PORTS = 32
 MAX_DIM = 256

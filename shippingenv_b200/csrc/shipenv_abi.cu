@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -65,9 +66,10 @@ struct shipenv_ctx {
   std::vector<unsigned char> h_world;
   uint32_t world_bytes = 0;
   bool dirty = true;
+  bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_step, occ_step_obs, occ_reset, occ_observe, occ_sample, occ_rollout;
+  Occ occ_step_fast, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout;
 };
 
 namespace {
@@ -98,6 +100,7 @@ int build_world(shipenv_ctx* c) {
     else { r = r + k.p_use_fuel; r = r + k.p_water; }
     if (idx & 1) r = r + k.r_closer; else r = r + k.p_farther;
     h->move_reward[idx] = r;
+    h->move_reward_f32[idx] = float(r);
   }
   for (int p = 0; p < c->P; ++p) {
     h->port[p] = uint32_t(c->px[p]) | (uint32_t(c->py[p]) << 8) | (uint32_t(c->pfuel[p]) << 16) |
@@ -109,6 +112,7 @@ int build_world(shipenv_ctx* c) {
     volatile double q = double(cg) / double(k.capacity);  // normalize(), shipping/util.py:6-8
     h->loss_thr[cg] = uint32_t(q * 4294967296.0);          // exact scaling, then floor
   }
+  h->loss_thr[k.capacity] = 0xFFFFFFFFu;
   for (int x = 0; x < c->W; ++x)
     for (int y = 0; y < c->H; ++y)
       if (c->passable[size_t(x) * c->H + y]) bits[size_t(x) * wpr + (y >> 5)] |= 1u << (y & 31);
@@ -186,6 +190,7 @@ int shipenv_ctx_create(int device, shipenv_ctx** out) {
   shipenv_ctx* c = new (std::nothrow) shipenv_ctx();
   if (!c) return fail(SHIPENV_E_ARG, "out of host memory");
   c->device = device;
+  { const char* e = getenv("SHIPENV_NO_FAST"); c->no_fast_kernel = e && e[0] == '1'; }
   CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   cudaError_t e = cudaMalloc(&c->d_world, kMaxWorldBytes);
@@ -272,6 +277,9 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   if (n < 0 || (n > 0 && (!ships || !clock || !actions))) return fail(SHIPENV_E_ARG, "step: null buffer or negative n");
   if (max_steps < 0 || max_steps > 65535) return fail(SHIPENV_E_ARG, "max_steps %d outside 0..65535", max_steps);
   if (n == 0) return 0;
+  if (n >= (int64_t(1) << 31)) return fail(SHIPENV_E_ARG, "step: at most 2^31-1 envs per launch");
+  if ((reinterpret_cast<uintptr_t>(ships) | reinterpret_cast<uintptr_t>(clock) | reinterpret_cast<uintptr_t>(actions)) & 15u)
+    return fail(SHIPENV_E_ARG, "step: ships, clock and actions must be 16-byte aligned (TMA bulk copies)");
   if ((flags & SHIPENV_F_AUTO_RESET) && c->P < 2) return fail(SHIPENV_E_STATE, "auto-reset needs at least 2 ports");
   DeviceGuard guard(c->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -282,20 +290,40 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   if (io) a.io = *io; else memset(&a.io, 0, sizeof(a.io));
   a.seed = seed; a.env_id_base = env_id_base; a.n = n; a.max_steps = max_steps; a.flags = flags; a.word0 = word0;
   a.obs_width = 6 + 4 * c->P;
+  for (int r = 0; r < 10; ++r) {
+    a.round_key[2 * r] = uint32_t(seed) + uint32_t(r) * kPhiloxW0;
+    a.round_key[2 * r + 1] = uint32_t(seed >> 32) + uint32_t(r) * kPhiloxW1;
+  }
   const int64_t tiles = (n + kThreads - 1) / kThreads;
+  const bool lean = !a.io.reward_f64 && !a.io.status && !a.io.taken && !a.io.ep_return;
   int grid = 0;
   if (a.io.obs) {
     if (reinterpret_cast<uintptr_t>(a.io.obs) & 15u) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
-    const size_t base = (size_t(c->world_bytes) + 127) & ~size_t(127);
+    const size_t base = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + ((kPipeBytes + 127) & ~size_t(127));
     const size_t tile_bytes = size_t(kThreads) * a.obs_width * 4;
-    a.obs_bufs = (base + 2 * tile_bytes <= 64 * 1024) ? 2 : 1;
+    a.obs_bufs = (base + 2 * tile_bytes <= 96 * 1024) ? 2 : 1;
     const size_t smem = base + a.obs_bufs * tile_bytes;
-    if (int rc = grid_for(c, step_kernel<true>, c->occ_step_obs, kThreads, smem, tiles, &grid)) return rc;
-    step_kernel<true><<<grid, kThreads, smem, stream>>>(a);
+    if (lean) {
+      if (int rc = grid_for(c, step_kernel<true, true>, c->occ_step_obs, kStepBlock, smem, tiles, &grid)) return rc;
+      step_kernel<true, true><<<grid, kStepBlock, smem, stream>>>(a);
+    } else {
+      if (int rc = grid_for(c, step_kernel<true, false>, c->occ_step_obs_full, kStepBlock, smem, tiles, &grid)) return rc;
+      step_kernel<true, false><<<grid, kStepBlock, smem, stream>>>(a);
+    }
+  } else if (lean && a.io.reward_f32 && a.io.done_bits && a.io.reset_bits && a.io.error_bits && word0 == 0 &&
+             c->P >= 2 && !c->no_fast_kernel) {
+    const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes + kDeferCap * 4 * (kThreads / 32);
+    if (int rc = grid_for(c, step_fast_kernel, c->occ_step_fast, kStepBlock, smem, tiles, &grid)) return rc;
+    step_fast_kernel<<<grid, kStepBlock, smem, stream>>>(a);
   } else {
-    const size_t smem = c->world_bytes;
-    if (int rc = grid_for(c, step_kernel<false>, c->occ_step, kThreads, smem, tiles, &grid)) return rc;
-    step_kernel<false><<<grid, kThreads, smem, stream>>>(a);
+    const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes;
+    if (lean) {
+      if (int rc = grid_for(c, step_kernel<false, true>, c->occ_step, kStepBlock, smem, tiles, &grid)) return rc;
+      step_kernel<false, true><<<grid, kStepBlock, smem, stream>>>(a);
+    } else {
+      if (int rc = grid_for(c, step_kernel<false, false>, c->occ_step_full, kStepBlock, smem, tiles, &grid)) return rc;
+      step_kernel<false, false><<<grid, kStepBlock, smem, stream>>>(a);
+    }
   }
   CUDA_TRY(cudaGetLastError());
   ++g_launches;

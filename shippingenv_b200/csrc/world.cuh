@@ -25,10 +25,12 @@ struct alignas(16) WorldHdr {
   // Reward of a MOVE before loss/arrival terms, accumulated on the host in the reference's
   // order (shipping/environment.py:288-315); index = out_of_fuel<<2 | ground<<1 | closer.
   double move_reward[8];
+  float move_reward_f32[8];      // the same, rounded once to f32 (the reward_f32 output)
   uint32_t port[kMaxPorts];      // x | y<<8 | fuel<<16 | cargo<<24
   float obs_tail[4 * kMaxPorts]; // constant tail of a preprocess_state row
   // loss_thr[c] = floor((c / capacity) * 2^32) evaluated in fp64 on the host: the draw
-  // `random() <= cargo / 50` (:318-320) is exactly `word <= loss_thr[cargo]` for cargo < capacity.
+  // `random() <= cargo / 50` (:318-320) is exactly `word <= loss_thr[cargo]` for cargo < capacity;
+  // loss_thr[capacity] = 0xFFFFFFFF (cargo >= capacity: the draw always succeeds).
   uint32_t loss_thr[kMaxCap];
 };
 static_assert(sizeof(WorldHdr) % 16 == 0, "world header must stay 16-byte sized for the bulk copy");
