@@ -9,6 +9,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstddef>
+
 #include "transition.cuh"
 
 namespace shipenv {
@@ -42,6 +44,40 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void consumer_sync() {  // the 8 consumer warps only (the producer warp has left)
   asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {   // shared-address forms
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITS_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONES_%=;\n"
+      "bra WAITS_%=;\n"
+      "DONES_%=:\n"
+      "}\n" ::"r"(bar_saddr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ int lds_s16(uint32_t saddr) {
+  short v;
+  asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return int(v);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -495,9 +531,13 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
     return;
   }
   // ---- consumers ----
+  // Everything the streaming loop touches in shared memory is addressed through 32-bit shared
+  // addresses computed once (ld.shared with immediate offsets, no generic-address arithmetic).
   const int lane = tid & 31;
   int* defer = defer_all + (tid >> 5) * kDeferCap;
   int n_defer = 0;                                   // warp-uniform
+  const uint32_t wb = smem_u32(smem);                // world blob
+  const uint32_t bits_b = wb + uint32_t(sizeof(WorldHdr));
   const uint32_t W = uint32_t(w.h->W), H = uint32_t(w.h->H), P = uint32_t(w.h->P);
   const uint32_t cap = uint32_t(w.h->capacity);
   const uint32_t wpr = uint32_t(w.h->wpr);
@@ -508,28 +548,46 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   uint32_t* const mask_ptr = lane == 0 ? a.io.done_bits : lane == 1 ? a.io.reset_bits : a.io.error_bits;
   const uint32_t reset_rec_y = uint32_t(w.h->cargo0);
   const uint32_t reset_rec_z = uint32_t(__double2loint(w.h->fuel0)), reset_rec_w = uint32_t(__double2hiint(w.h->fuel0));
+  const uint32_t stage_b = smem_u32(stage);
+  const uint32_t my_ship = stage_b + uint32_t(tid) * 16u;
+  const uint32_t my_clock = stage_b + 4096u + uint32_t(tid) * 4u;
+  const uint32_t my_act = stage_b + 5120u + uint32_t(tid) * 2u;
+  const uint32_t full_b = smem_u32(full_bar), empty_b = smem_u32(empty_bar);
+  const int full_tiles = n / kThreads;               // tiles below this index are complete
 
-  int tile = blockIdx.x, it = 0;
+  int tile = blockIdx.x;
+  uint32_t st = 0, parity = 0;                       // pipeline slot of `tile` and its phase parity
   while (true) {
     // ------------------------------ streaming loop: no calls in here ------------------------------
-    for (; tile < n_tiles && n_defer <= kDeferCap - 32; tile += gridDim.x, ++it) {
+    for (; tile < n_tiles && n_defer <= kDeferCap - 32; tile += gridDim.x) {
       const int i = tile * kThreads + tid;
-      const bool live = i < n;
-      const int st = it % kStages;
-      uint4 rec = make_uint4(0, 0, 0, 0);
-      uint32_t c = 0;
-      int act = 0;
-      mbar_wait(&full_bar[st], uint32_t(it / kStages) & 1u);
-      if (tid < (min(kThreads, n - tile * kThreads) & ~7)) {
-        rec = stage[st].ships[tid]; c = stage[st].clock[tid]; act = stage[st].act[tid];
-      } else if (live) {             // ragged tail of the last tile
-        rec = ld_stream_u4(a.ships + i); c = ld_stream_u32(a.clock + i); act = ld_stream_s16(a.actions + i);
+      bool live = true;
+      uint4 rec;
+      uint32_t c;
+      int act;
+      mbar_wait_s(full_b + st * 8u, parity);
+      if (tile < full_tiles) {
+        const uint32_t so = st * uint32_t(sizeof(TileStage));
+        rec = lds_u4(my_ship + so); c = lds_u32(my_clock + so); act = lds_s16(my_act + so);
+      } else {                       // the ragged last tile: rows beyond the 8-row units come straight from HBM
+        live = i < n;
+        rec = make_uint4(0, 0, 0, 0); c = 0; act = 0;
+        if (tid < ((n - tile * kThreads) & ~7)) {
+          rec = stage[st].ships[tid]; c = stage[st].clock[tid]; act = stage[st].act[tid];
+        } else if (live) {
+          rec = ld_stream_u4(a.ships + i); c = ld_stream_u32(a.clock + i); act = ld_stream_s16(a.actions + i);
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[st]);
+      if (lane == 0) mbar_arrive_s(empty_b + st * 8u);
+      st = (st + 1u) & uint32_t(kStages - 1);
+      parity ^= uint32_t(st == 0u);
 
       const uint32_t x = rec.x & 255u, y = (rec.x >> 8) & 255u, dest = rec.x >> 24;
-      const uint32_t nx = x + uint32_t(act == 3) - uint32_t(act == 1), ny = y + uint32_t(act == 2) - uint32_t(act == 0);
+      // N,E,S,W = (0,-1),(-1,0),(0,1),(1,0): odd actions move along x, even ones along y
+      const int m = act & 3;
+      const int dx = (m & 1) * (m - 2), dy = ((m & 1) ^ 1) * (m - 1);
+      const uint32_t nx = x + uint32_t(dx), ny = y + uint32_t(dy);
       const bool is_move = unsigned(act) < 4u && dest != uint32_t(kNone);
       const bool in_map = nx < W && ny < H;          // unsigned: -1 wraps to a huge value  (:284)
       // Philox block 0 of the (env, clock) cell: words 0,1 = fuel-cost and cargo-loss draws, 2,3 = reset draws
@@ -542,14 +600,14 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const double fuel = __hiloint2double(int(rec.w), int(rec.z));
       const bool no_fuel = fuel < cost;                                                   // :288
       const uint32_t cell = in_map ? nx * wpr + (ny >> 5) : 0u;
-      const bool water = (w.bits[cell] >> (ny & 31u)) & 1u;                               // :293
-      const uint32_t pd = w.h->port[dest & 31u];
+      const bool water = (lds_u32(bits_b + cell * 4u) >> (ny & 31u)) & 1u;                // :293
+      const uint32_t pd = lds_u32(wb + uint32_t(offsetof(WorldHdr, port)) + (dest & 31u) * 4u);
       const uint32_t tx = pd & 255u, ty = (pd >> 8) & 255u;
-      const int ax = int(x) - int(tx), ay = int(y) - int(ty), bx = int(nx) - int(tx), by = int(ny) - int(ty);
-      const bool closer = ax * ax + ay * ay > bx * bx + by * by;                          // :309-312
+      // closer <=> d_prev - d_new > 0 <=> (x - tx) * dx + (y - ty) * dy < 0 for a unit move   (:309-312)
+      const bool closer = (int(x) - int(tx)) * dx + (int(y) - int(ty)) * dy < 0;
       const uint32_t px = water ? nx : x, py = water ? ny : y;
       // loss_thr[cap] = 0xFFFFFFFF: cargo >= capacity always draws; negative cargo goes the general way
-      const bool trigger = wd[1] <= w.h->loss_thr[min(uint32_t(rec.y), cap)];             // :318-320
+      const bool trigger = wd[1] <= lds_u32(wb + uint32_t(offsetof(WorldHdr, loss_thr)) + min(uint32_t(rec.y), cap) * 4u);  // :318-320
       const bool arrive = px == tx && py == ty;                                           // :325
       const uint32_t c1 = c + 1u;
       const bool do_reset = auto_reset && (no_fuel || (c1 & 0xFFFFu) >= trunc_at);
@@ -557,7 +615,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const bool general = live && (!is_move || (in_map && (trigger || arrive || (do_reset && ro == rd))));
       const bool ok = live && is_move && in_map && !general;
       const bool off_map = live && is_move && !in_map;
-      if (ok) {
+      {
         const double fuel1 = water ? __dsub_rn(fuel, cost) : fuel;                        // :298
         uint4 out;
         out.x = px | (py << 8) | (rec.x & 0xFFFF0000u);
@@ -565,16 +623,17 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         out.z = uint32_t(__double2loint(fuel1)); out.w = uint32_t(__double2hiint(fuel1));
         uint32_t c_out = c1;
         if (do_reset) {                                                                   // :227-243
-          out.x = (w.h->port[ro] & 0xFFFFu) | (ro << 16) | (rd << 24);
+          out.x = (lds_u32(wb + uint32_t(offsetof(WorldHdr, port)) + ro * 4u) & 0xFFFFu) | (ro << 16) | (rd << 24);
           out.y = reset_rec_y; out.z = reset_rec_z; out.w = reset_rec_w;
           c_out = ((c >> 16) + 1u) << 16;
         }
-        st_stream_u4(a.ships + i, out);
-        a.clock[i] = c_out;
-      }
-      if (live && !general) {
-        const float r = w.h->move_reward_f32[(uint32_t(no_fuel) << 2) | (uint32_t(!water) << 1) | uint32_t(closer)];
-        a.io.reward_f32[i] = ok ? r : 0.f;
+        const float r = lds_f32(wb + uint32_t(offsetof(WorldHdr, move_reward_f32)) +
+                                ((uint32_t(no_fuel) << 2) | (uint32_t(!water) << 1) | uint32_t(closer)) * 4u);
+        if (ok) {
+          st_stream_u4(a.ships + i, out);
+          a.clock[i] = c_out;
+        }
+        if (live && !general) a.io.reward_f32[i] = ok ? r : 0.f;
       }
       const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, ok && no_fuel);
       const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, ok && do_reset);
