@@ -7,3 +7,5 @@ There is no CPU fallback; importing works anywhere, constructing an environment 
 from ._native import ShipEnvError, launch_count  # noqa: F401
 from .batched import (BatchedEnvironment, StepResult, unpack_bits, DEFAULT_PORTS,  # noqa: F401
                       DEFAULT_PORT_FUEL, DEFAULT_PORT_CARGO)
+from .environment import Environment  # noqa: F401
+from .types import ActionType, Color, Entity, Initial, Penalty, Reward, ShipMove  # noqa: F401

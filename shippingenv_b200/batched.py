@@ -14,6 +14,7 @@ import torch
 
 from . import _native as nat
 from .mapio import derive_grid, passable_of
+from .stats import new_stats, reduce_stats, summarize
 
 # reference defaults: utils/constants.py:57-63 and the seed-2024 stock draw
 DEFAULT_PORTS = [[41, 40], [60, 22], [78, 29], [49, 72], [62, 72]]
@@ -97,7 +98,7 @@ class BatchedEnvironment:
         self.ep_return = self.stats = None
         if track_stats:
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
-            self.stats = torch.tensor([0, 0, 0, 0, -float("inf"), float("inf")], dtype=torch.float64, device=dev)
+            self.stats = new_stats(dev)
         self._policy = None
 
     # ---- views of the ship records ------------------------------------------------------
@@ -203,6 +204,12 @@ class BatchedEnvironment:
         self.ctx.rollout(roots.data_ptr(), R, sims, max_steps, ret.data_ptr(), _ptr(final), steps.data_ptr(),
                          status.data_ptr(), self.seed, base, self._stream())
         return dict(returns=ret, final=final, steps=steps, status=status)
+
+    def episode_summary(self, group=None):
+        """Episode statistics since construction, reduced over the process group (the one collective)."""
+        if self.stats is None:
+            raise ValueError("construct with track_stats=True")
+        return summarize(reduce_stats(self.stats, group))
 
     # ---- host <-> device state ----------------------------------------------------------
     def load_state(self, ships_np, clock_np=None):

@@ -1,0 +1,301 @@
+"""``Environment``: the reference's single-ship Python API (shipping/environment.py:28-376) on the
+sm_100a kernels.  It is the N=1 view of the batched path: every transition, reset and
+``sample_action`` is computed by ``libshipenv.so`` on the GPU; this class only keeps the Python
+attributes the agents read and write and turns status codes back into the reference's exceptions.
+
+Contract: the attributes are the source of truth.  Agents assign them wholesale
+(agents/mcts.py:199-208), so before every launch the ship record is packed from the attributes
+and after it they are refreshed from the device.  The world (map + port table) is re-uploaded
+only when it changed.
+
+Differences from the reference, all documented in DESIGN.md: draws come from the Philox word
+stream (seeded from ``random`` at construction unless ``seed`` is given) instead of MT19937;
+moves must be one of the four unit moves; ``reset`` with fewer than two ports raises instead of
+looping forever; ``sample_action`` with ``fuel == 0`` at a port raises ``TypeError`` like the
+reference does, but never consumes a draw.
+"""
+import random as _pyrandom
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .mapio import derive_grid
+from .types import ActionType, Color, Entity, Initial, MOVE_INDEX, MOVES, Penalty, Reward, ShipMove  # noqa: F401
+
+_ERRORS = {
+    nat.ST_OFF_MAP: (ValueError, "Move is out of range"),                                     # :284
+    nat.ST_NO_DEST: (Exception, "Cannot move without destination port"),                      # :276
+    nat.ST_SEL_RANGE: (IndexError, "Port index is out of range"),                             # :269
+    nat.ST_SEL_ORIGIN: (Exception, "Destination port must be different from current one"),    # :267
+    nat.ST_NOT_AT_PORT: (Exception, "Not currently at port"),                                 # :343,352
+    nat.ST_BAD_AMOUNT: (ValueError, "Invalid fuel amount"),                                   # :346,355
+    nat.ST_UNKNOWN: (ValueError, "Action category unknown"),                                  # :374
+    nat.ST_NO_PORTS: (Exception, "No ports available"),                                       # :360
+    nat.ST_SAMPLE_CRASH: (TypeError, "'float' object is not subscriptable"),                  # :163
+}
+
+# byte offsets inside the per-instance 128-byte device / pinned-host block
+_SHIP, _REWARD, _CLOCK, _ACTION, _DONE, _RESET, _ERR, _STATUS, _TAKEN, _WORDS, _BLOCK = 0, 16, 32, 48, 64, 68, 72, 76, 78, 80, 128
+
+_contexts = {}   # device index -> (Context, world signature currently uploaded)
+
+
+def _context(device_index):
+    if device_index not in _contexts:
+        _contexts[device_index] = [nat.Context(device_index), None]
+    return _contexts[device_index]
+
+
+class Environment:
+    def __init__(self, map_path, game_size=(100, 100), seed=None, device=None, env_id=0):
+        # ** Configurations (shipping/environment.py:29-43)
+        self.size_game = game_size
+        self.port_positions = []
+        self.port_fuel = []
+        self.port_cargo = []
+        self.ship_position = []
+        self.cargo = Initial.CARGO
+        self.fuel = Initial.FUEL
+        self.origin_port_index = None
+        self.destination_port_index = None
+        self.np_game = derive_grid(map_path, game_size)      # raises FileNotFoundError like :47
+
+        if not torch.cuda.is_available():
+            raise nat.ShipEnvError("Environment needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._device = torch.device(device if device is not None else "cuda")
+        if self._device.index is None:
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        self._seed = _pyrandom.getrandbits(64) if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._env_id = int(env_id)
+        self._clock = 0          # episode << 16 | step: selects the Philox cell of the next step
+        self._word = 0           # words of that cell already consumed by sample_action()
+        self._dev = torch.zeros(_BLOCK, dtype=torch.uint8, device=self._device)
+        self._host = torch.zeros(_BLOCK, dtype=torch.uint8).pin_memory()
+        self._hnp = self._host.numpy()
+        self._passable_key = None
+        self._passable = None
+
+    # ------------------------------------------------------------------ construction
+    def _is_within_map(self, x, y):
+        return 0 <= x < self.size_game[0] and 0 <= y < self.size_game[1]
+
+    def add_port(self, pos):
+        x, y = pos[0], pos[1]
+        if not self._is_within_map(x, y):
+            raise ValueError("Coordinates not within map")
+        fuel, cargo = nat.port_stock(self._seed, len(self.port_positions))   # randint(5, 20) twice, :63-64
+        self.port_positions.append(pos)
+        self.port_fuel.append(fuel)
+        self.port_cargo.append(cargo)
+        self.np_game[x, y] = Entity.PORT
+
+    def remove_port(self, idx):
+        # the reference compares an int with a list here and always raises TypeError (:68)
+        if 0 <= idx < self.port_positions and 0 <= idx < self.port_cargo:
+            raise AssertionError("unreachable")
+        raise IndexError("Invalid index")
+
+    # ------------------------------------------------------------------ host <-> device
+    def _sync_world(self):
+        key = (id(self.np_game), len(self.port_positions))
+        if key != self._passable_key:
+            g = np.asarray(self.np_game)
+            if g.ndim != 2 or g.shape[0] < self.size_game[0] or g.shape[1] < self.size_game[1]:
+                raise ValueError("np_game does not cover size_game (non-square maps are not supported)")
+            self._passable = np.ascontiguousarray(g[:self.size_game[0], :self.size_game[1]] != Entity.GROUND,
+                                                  dtype=np.uint8)
+            self._passable_key = key
+        ports = [(int(p[0]), int(p[1])) for p in self.port_positions]
+        sig = (self._passable.tobytes(), tuple(ports), tuple(map(int, self.port_fuel)),
+               tuple(map(int, self.port_cargo)))
+        slot = _context(self._device.index)
+        if slot[1] != sig:
+            if len(ports) > nat.MAX_PORTS:
+                raise ValueError(f"at most {nat.MAX_PORTS} ports")
+            slot[0].set_map(self._passable)
+            slot[0].set_ports(ports, list(map(int, self.port_fuel)), list(map(int, self.port_cargo)))
+            slot[1] = sig
+        return slot[0]
+
+    def _pack(self, action=0):
+        h = self._hnp
+        pos = self.ship_position if len(self.ship_position) == 2 else (0, 0)
+        h[0], h[1] = int(pos[0]) & 255, int(pos[1]) & 255
+        h[2] = nat.NONE_PORT if self.origin_port_index is None else int(self.origin_port_index)
+        h[3] = nat.NONE_PORT if self.destination_port_index is None else int(self.destination_port_index)
+        h[4:8].view(np.int32)[0] = int(self.cargo)
+        h[8:16].view(np.float64)[0] = float(self.fuel)
+        h[_CLOCK:_CLOCK + 4].view(np.uint32)[0] = self._clock
+        h[_ACTION:_ACTION + 2].view(np.int16)[0] = action
+        self._dev[:_DONE].copy_(self._host[:_DONE], non_blocking=True)
+
+    def _unpack(self):
+        self._host.copy_(self._dev, non_blocking=False)
+        h = self._hnp
+        return (int(h[0]), int(h[1]), int(h[2]), int(h[3]), int(h[4:8].view(np.int32)[0]),
+                float(h[8:16].view(np.float64)[0]))
+
+    def _ptr(self, off):
+        return self._dev.data_ptr() + off
+
+    def _stream(self):
+        return torch.cuda.current_stream(self._device).cuda_stream
+
+    def _adopt(self, x, y, origin, dest, cargo, fuel, keep_int_fuel):
+        self.origin_port_index = None if origin == nat.NONE_PORT else origin
+        self.destination_port_index = None if dest == nat.NONE_PORT else dest
+        self.cargo = cargo
+        self.fuel = int(fuel) if keep_int_fuel and fuel == int(fuel) else fuel
+        return x, y
+
+    # ------------------------------------------------------------------ the reference API
+    def _get_current_port_idx(self):
+        for idx, port_position in enumerate(self.port_positions):
+            if port_position == self.ship_position:
+                return idx
+        return None
+
+    def _build_state(self):
+        ship = {
+            "position": self.ship_position,
+            "fuel": self.fuel,
+            "cargo": self.fuel,          # sic: the reference copies fuel here (:206); observation parity
+            "origin_port_index": self.origin_port_index,
+            "destination_port_index": self.destination_port_index,
+        }
+        ports = [{"index": idx, "position": p, "fuel": self.port_fuel[idx], "cargo": self.port_cargo[idx]}
+                 for idx, p in enumerate(self.port_positions)]
+        return {"ship": ship, "ports": ports}
+
+    def reset(self):
+        if len(self.port_positions) == 0:
+            raise Exception("No ports available")                    # _sample_random_port, :156
+        if len(self.port_positions) < 2:
+            raise ValueError("reset needs at least two ports (the reference loops forever with one)")
+        ctx = self._sync_world()
+        self.np_game[(self.np_game == Entity.BOAT) | (self.np_game == Entity.TRAVEL)] = Entity.WATER
+        self._pack()
+        ctx.reset(self._ptr(_SHIP), self._ptr(_CLOCK), self._seed, self._env_id, 1, None, self._stream())
+        x, y, origin, dest, cargo, fuel = self._unpack()
+        self._clock = int(self._hnp[_CLOCK:_CLOCK + 4].view(np.uint32)[0])
+        self._word = 0
+        self._adopt(x, y, origin, dest, cargo, fuel, keep_int_fuel=True)
+        current_port = self.port_positions[origin]
+        self.np_game[current_port[0], current_port[1]] = Entity.BOAT
+        self.ship_position = current_port                            # aliases the port's list, like :241
+        return self._build_state()
+
+    def sample_action(self):
+        ctx = self._sync_world()
+        self._pack()
+        ctx.sample_action(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_TAKEN), self._ptr(_WORDS),
+                          self._ptr(_STATUS), self._seed, self._env_id, 1, self._word, self._stream())
+        self._host.copy_(self._dev, non_blocking=False)
+        h = self._hnp
+        status = int(h[_STATUS])
+        if status != nat.ST_OK:
+            exc, msg = _ERRORS[status]
+            raise exc(msg)
+        self._word += int(h[_WORDS])
+        return self._decode(int(h[_TAKEN:_TAKEN + 2].view(np.int16)[0]))
+
+    def _decode(self, a):
+        P = len(self.port_positions)
+        if a < 4:
+            return [ActionType.MOVE_SHIP, MOVES[a]]
+        if a < 4 + P:
+            return [ActionType.SELECT_PORT, a - 4]
+        if a < 4 + P + nat.N_CARGO_ACTIONS:
+            return [ActionType.TAKE_CARGO, a - (4 + P)]
+        if a < 4 + P + nat.N_CARGO_ACTIONS + nat.N_FUEL_ACTIONS:
+            return [ActionType.TAKE_FUEL, a - (4 + P + nat.N_CARGO_ACTIONS)]
+        if a < nat.ACT_EXT_FUEL:
+            return [ActionType.TAKE_CARGO, a - nat.ACT_EXT_CARGO]
+        return [ActionType.TAKE_FUEL, a - nat.ACT_EXT_FUEL]
+
+    def _encode(self, action):
+        """[category, value] -> device action index; raises what the reference raises before any draw."""
+        P = len(self.port_positions)
+        category, value = action
+        if category == ActionType.MOVE_SHIP:
+            if len(value) != 2:
+                raise ValueError("Move needs to be of format (x,y) or [x, y]")       # :274
+            if self.destination_port_index is None:
+                raise Exception("Cannot move without destination port")               # :276
+            key = (int(value[0]), int(value[1]))
+            if key not in MOVE_INDEX:
+                raise NotImplementedError("only the four unit moves of ShipMove run on the device")
+            return MOVE_INDEX[key]
+        if category == ActionType.SELECT_PORT:
+            if not 0 <= value < P:
+                raise IndexError("Port index is out of range")                        # :269
+            return 4 + int(value)
+        if category in (ActionType.TAKE_CARGO, ActionType.TAKE_FUEL):
+            if value != int(value):
+                raise NotImplementedError("fractional amounts are not supported on the device")
+            v = min(max(int(value), 0), 8191)      # anything outside 1..255 is rejected by the kernel as well
+            if category == ActionType.TAKE_CARGO:
+                return 4 + P + v if v < nat.N_CARGO_ACTIONS else nat.ACT_EXT_CARGO + v
+            return 4 + P + nat.N_CARGO_ACTIONS + v if v < nat.N_FUEL_ACTIONS else nat.ACT_EXT_FUEL + v
+        raise ValueError("Action category unknown")                                   # :374
+
+    def step(self, action):
+        if len(self.port_positions) == 0:
+            raise Exception("No ports available")                                     # :360
+        a = self._encode(action)
+        ctx = self._sync_world()
+        old = (int(self.ship_position[0]), int(self.ship_position[1])) if len(self.ship_position) == 2 else None
+        fuel_was_int = isinstance(self.fuel, int)
+        self._pack(a)
+        io = nat.StepIO()
+        io.reward_f64, io.status = self._ptr(_REWARD), self._ptr(_STATUS)
+        io.done_bits, io.reset_bits, io.error_bits = self._ptr(_DONE), self._ptr(_RESET), self._ptr(_ERR)
+        ctx.step(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_ACTION), io, self._seed, self._env_id, 1, 0, 0,
+                 self._word, self._stream())
+        x, y, origin, dest, cargo, fuel = self._unpack()
+        h = self._hnp
+        status = int(h[_STATUS])
+        if status != nat.ST_OK:       # nothing changed on the device, no draw was consumed
+            exc, msg = _ERRORS[status]
+            raise exc(msg)
+        self._clock = int(h[_CLOCK:_CLOCK + 4].view(np.uint32)[0])
+        self._word = 0
+        moved = (x, y) != old
+        keep_int = fuel_was_int and not (action[0] == ActionType.MOVE_SHIP and moved)
+        self._adopt(x, y, origin, dest, cargo, fuel, keep_int_fuel=keep_int)
+        if moved:
+            self.ship_position = [x, y]                                               # a fresh list, like :297
+            self.np_game[old[0], old[1]] = Entity.TRAVEL                              # :303-304
+            self.np_game[x, y] = Entity.BOAT
+        reward = float(h[_REWARD:_REWARD + 8].view(np.float64)[0])
+        done = bool(h[_DONE] & 1)
+        return self._build_state(), reward, done, {}
+
+    # ------------------------------------------------------------------ rendering (host, cv2; not on the hot path)
+    def render_real_time(self, render_size=(355, 533)):
+        import cv2
+        g = self.np_game
+        img = np.zeros((g.shape[0], g.shape[1], 3), dtype="uint8")
+        for code, color in ((Entity.WATER, Color.WATER), (Entity.GROUND, Color.GROUND), (Entity.PORT, Color.PORT),
+                            (Entity.DESTINY_PORT, Color.DESTINY_PORT), (Entity.TRAVEL, Color.TRAVEL)):
+            img[g == code] = color
+        bx, by = np.where(g == Entity.BOAT)
+        if len(bx) > 0:
+            x, y = bx[0], by[0]
+            img[x, y - 3:y + 3, :] = Color.BOAT
+            img[x + 1, y - 2:y + 2, :] = Color.BOAT
+            img[x - 4:x, y, :] = Color.BLACK
+            img[x - 4:x - 1, y + 1, :] = Color.WHITE
+            img[x - 3, y + 2, :] = Color.WHITE
+        frame = cv2.resize(img, render_size, interpolation=cv2.INTER_AREA)
+        font = cv2.FONT_HERSHEY_SIMPLEX
+        cv2.putText(frame, f"Fuel: {self.fuel:.2f}", (10, 20), font, 0.5, (255, 255, 255), 1, cv2.LINE_AA)
+        cv2.putText(frame, f"Cargo: {self.cargo}", (10, 40), font, 0.5, (255, 255, 255), 1, cv2.LINE_AA)
+        for idx in range(len(self.port_positions)):
+            cv2.putText(frame, f"P{idx + 1} - Cargo: {self.port_cargo[idx]} - Fuel: {self.port_fuel[idx]}",
+                        (10, 80 + 20 * idx), font, 0.5, (255, 255, 255), 1, cv2.LINE_AA)
+        cv2.imshow("Environment", frame)
+        if cv2.waitKey(100) == ord("q"):
+            cv2.destroyAllWindows()
+            raise SystemExit

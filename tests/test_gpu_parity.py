@@ -197,3 +197,32 @@ def test_cuda_consts_can_vary(torch_cuda, default_map):
         ref = o.step(ships, clock, np.full(n, -1, np.int16), seed, 0, 90, True)
         assert env.state_numpy()[0].tobytes() == ships.tobytes(), t
         assert (r.reward64.cpu().numpy().view(np.uint64) == ref["reward"].view(np.uint64)).all(), t
+
+
+def test_cuda_episode_statistics(torch_cuda, default_map):
+    """On-device episode return / length accumulators against the same quantities computed from the oracle."""
+    from shippingenv_b200 import BatchedEnvironment
+    n, seed, max_steps, T = 3000, 21, 37, 150
+    env = BatchedEnvironment(n, passable=default_map["passable"], seed=seed, device="cuda:0", max_steps=max_steps,
+                             track_stats=True)
+    o = orc.Oracle(default_map["passable"], env.ports, env.port_fuel, env.port_cargo)
+    ships, clock = np.zeros(n, orc.SHIP_DTYPE), np.zeros(n, np.uint32)
+    env.reset(); o.reset(ships, clock, seed)
+    ep = np.zeros(n)
+    rets, lens = [], []
+    for t in range(T):
+        before = clock.copy()
+        env.step_policy()
+        ref = o.step(ships, clock, np.full(n, -1, np.int16), seed, 0, max_steps, True)
+        ok = ref["status"] == 0
+        ep[ok] += ref["reward"][ok]
+        ended = ref["reset"] == 1
+        rets += ep[ended].tolist()
+        lens += ((before[ended] + 1) & 0xFFFF).tolist()
+        ep[ended] = 0.0
+    s = env.episode_summary()
+    assert s["total_episodes"] == len(rets) > n and s["total_steps"] == sum(lens)
+    assert abs(s["mean_reward"] - np.mean(rets)) < 1e-9 and abs(s["std_reward"] - np.std(rets)) < 1e-6
+    assert s["max_reward"] == max(rets) and s["min_reward"] == min(rets)
+    assert np.allclose(env.ep_return.cpu().numpy(), ep, rtol=0, atol=1e-12)
+    assert env.state_numpy()[0].tobytes() == ships.tobytes()
