@@ -100,6 +100,10 @@ class BatchedEnvironment:
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
             self.stats = new_stats(dev)
         self._policy = None
+        self._step_cache, self._io_keepalive = {}, []
+        self._lib_step = nat.lib().shipenv_step
+        self._ctx_handle = self.ctx._h
+        self._ships_ptr, self._clock_ptr = self.ships.data_ptr(), self.clock.data_ptr()
 
     # ---- views of the ship records ------------------------------------------------------
     @property
@@ -140,6 +144,21 @@ class BatchedEnvironment:
             raise ValueError("actions must be an int16 tensor of shape [num_envs] on the env's device")
         if not actions.is_contiguous():
             actions = actions.contiguous()
+        key = (want_obs, want_status, want_taken, want_reward64, None if obs_out is None else obs_out.data_ptr())
+        cached = self._step_cache.get(key)
+        if cached is None:
+            cached = self._step_cache[key] = self._build_step_io(want_obs, want_status, want_taken, want_reward64,
+                                                                 obs_out)
+        io_ref, res = cached
+        rc = self._lib_step(self._ctx_handle, self._ships_ptr, self._clock_ptr, actions.data_ptr(), io_ref, self.seed,
+                            self.env_id_base, self.n, self.max_steps, nat.F_AUTO_RESET if self.auto_reset else 0,
+                            word0, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            nat.check(rc)
+        return res
+
+    def _build_step_io(self, want_obs, want_status, want_taken, want_reward64, obs_out):
+        import ctypes
         io = nat.StepIO()
         io.reward_f32 = self.reward.data_ptr()
         io.done_bits, io.reset_bits, io.error_bits = (self.done_bits.data_ptr(), self.reset_bits.data_ptr(),
@@ -162,10 +181,8 @@ class BatchedEnvironment:
             io.obs = res.obs.data_ptr()
         if self.ep_return is not None:
             io.ep_return, io.stats = self.ep_return.data_ptr(), self.stats.data_ptr()
-        flags = nat.F_AUTO_RESET if self.auto_reset else 0
-        self.ctx.step(self.ships.data_ptr(), self.clock.data_ptr(), actions.data_ptr(), io, self.seed,
-                      self.env_id_base, self.n, self.max_steps, flags, word0, self._stream())
-        return res
+        self._io_keepalive.append(io)
+        return ctypes.byref(io), res
 
     def step_policy(self, **kw):
         """One step of the reference's random policy (``sample_action`` + retry) on every env."""
