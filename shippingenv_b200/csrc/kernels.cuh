@@ -25,7 +25,7 @@ struct alignas(16) TileStage {  // one 256-env tile, filled by three TMA bulk co
   int16_t act[kThreads];
 };
 static_assert(sizeof(TileStage) == 5632, "stage layout");
-constexpr size_t kPipeBytes = sizeof(TileStage) * kStages + 2 * 8 * kStages;  // slots + full/empty mbarriers
+constexpr size_t kPipeBytes = sizeof(TileStage) * kStages + 2 * 8 * kStages + 4 * kStages;  // slots + full/empty mbarriers + tile ids
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA bulk copies (cp.async.bulk; SASS UBLKCP)
@@ -55,6 +55,19 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity)
       "bra WAITS_%=;\n"
       "DONES_%=:\n"
       "}\n" ::"r"(bar_saddr), "r"(parity) : "memory");
+}
+// producer-side wait: sleeps between polls so that the waiting warp does not eat issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITB_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONEB_%=;\n"
+      "nanosleep.u32 256;\n"
+      "bra WAITB_%=;\n"
+      "DONEB_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
@@ -171,6 +184,8 @@ struct StepArgs {
   int obs_width;            // 6 + 4P
   int obs_bufs;             // observation tiles resident in shared memory (1 or 2)
   uint32_t round_key[20];   // Philox round keys of `seed`: (k0 + r*W0, k1 + r*W1), r = 0..9
+  uint32_t* tile_counter;   // step_fast_kernel: global ticket counter (context-owned, never reset)
+  uint32_t tile_base;       // ticket value this launch starts at
 };
 
 // Philox4x32-10 with the round keys precomputed on the host: 20 IMAD.WIDE + 20 LOP3.
@@ -495,41 +510,51 @@ constexpr int kDeferCap = 64;   // per-warp deferred-env list; a tile adds at mo
 __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
-  stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
   const int tid = threadIdx.x;
   const int n = int(a.n);
-  const int n_tiles = (n + kThreads - 1) / kThreads;
+  const int full_tiles = n / kThreads;               // the streaming loop takes complete tiles only
   TileStage* stage = reinterpret_cast<TileStage*>(smem + ((a.world_bytes + 127u) & ~127u));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage) + sizeof(TileStage) * kStages);
   uint64_t* empty_bar = full_bar + kStages;
-  int* defer_all = reinterpret_cast<int*>(empty_bar + kStages);
+  volatile int* stage_tile = reinterpret_cast<volatile int*>(empty_bar + kStages);   // tile index held by each slot
+  int* defer_all = const_cast<int*>(stage_tile) + kStages;
   if (tid == 0) {
+    mbar_init(&world_bar, 1);
 #pragma unroll
     for (int st = 0; st < kStages; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], kThreads / 32); }
     fence_proxy_async();
   }
   __syncthreads();
+  if (tid == 0) {                    // the world blob and the first tiles are fetched concurrently
+    mbar_expect_tx(&world_bar, a.world_bytes);
+    tma_load_bulk(smem, a.world, a.world_bytes, &world_bar);
+  }
   if (tid >= kThreads) {             // ---- producer warp: lane 0 streams tiles in with TMA ----
     if (tid == kThreads) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      // Tiles are handed out by a global ticket counter, so SMs that run ahead simply take more tiles
+      // (no tail imbalance).  The counter is never reset: the host passes the ticket this launch starts at.
+      uint32_t ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base;
+      for (int it = 0;; ++it) {
         const int st = it % kStages;
-        if (it >= kStages) mbar_wait(&empty_bar[st], uint32_t(it / kStages - 1) & 1u);
-        const int base = tile * kThreads;
-        const int rows8 = min(kThreads, n - base) & ~7;
-        if (rows8 > 0) {
-          mbar_expect_tx(&full_bar[st], uint32_t(rows8) * 22u);
-          tma_load_bulk(stage[st].ships, a.ships + base, uint32_t(rows8) * 16u, &full_bar[st]);
-          tma_load_bulk(stage[st].clock, a.clock + base, uint32_t(rows8) * 4u, &full_bar[st]);
-          tma_load_bulk(stage[st].act, a.actions + base, uint32_t(rows8) * 2u, &full_bar[st]);
-        } else {
+        if (it >= kStages) mbar_wait_backoff(&empty_bar[st], uint32_t(it / kStages - 1) & 1u);
+        if (ticket >= uint32_t(full_tiles)) {          // out of tiles: publish the end marker
+          stage_tile[st] = -1;
           mbar_arrive(&full_bar[st]);
+          break;
         }
+        const int base = int(ticket) * kThreads;
+        stage_tile[st] = int(ticket);
+        mbar_expect_tx(&full_bar[st], uint32_t(sizeof(TileStage)));
+        tma_load_bulk(stage[st].ships, a.ships + base, kThreads * 16u, &full_bar[st]);
+        tma_load_bulk(stage[st].clock, a.clock + base, kThreads * 4u, &full_bar[st]);
+        tma_load_bulk(stage[st].act, a.actions + base, kThreads * 2u, &full_bar[st]);
+        ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base;   // in flight while the slot is awaited
       }
     }
     return;
   }
+  mbar_wait(&world_bar, 0);
   // ---- consumers ----
   // Everything the streaming loop touches in shared memory is addressed through 32-bit shared
   // addresses computed once (ld.shared with immediate offsets, no generic-address arithmetic).
@@ -553,31 +578,21 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   const uint32_t my_clock = stage_b + 4096u + uint32_t(tid) * 4u;
   const uint32_t my_act = stage_b + 5120u + uint32_t(tid) * 2u;
   const uint32_t full_b = smem_u32(full_bar), empty_b = smem_u32(empty_bar);
-  const int full_tiles = n / kThreads;               // tiles below this index are complete
 
-  int tile = blockIdx.x;
-  uint32_t st = 0, parity = 0;                       // pipeline slot of `tile` and its phase parity
+  const uint32_t tile_b = smem_u32(const_cast<int*>(stage_tile));
+  bool more = true;                                  // warp-uniform: the end marker has not been seen yet
+  uint32_t st = 0, parity = 0;                       // next pipeline slot and its phase parity
   while (true) {
     // ------------------------------ streaming loop: no calls in here ------------------------------
-    for (; tile < n_tiles && n_defer <= kDeferCap - 32; tile += gridDim.x) {
-      const int i = tile * kThreads + tid;
-      bool live = true;
-      uint4 rec;
-      uint32_t c;
-      int act;
+    while (more && n_defer <= kDeferCap - 32) {
       mbar_wait_s(full_b + st * 8u, parity);
-      if (tile < full_tiles) {
-        const uint32_t so = st * uint32_t(sizeof(TileStage));
-        rec = lds_u4(my_ship + so); c = lds_u32(my_clock + so); act = lds_s16(my_act + so);
-      } else {                       // the ragged last tile: rows beyond the 8-row units come straight from HBM
-        live = i < n;
-        rec = make_uint4(0, 0, 0, 0); c = 0; act = 0;
-        if (tid < ((n - tile * kThreads) & ~7)) {
-          rec = stage[st].ships[tid]; c = stage[st].clock[tid]; act = stage[st].act[tid];
-        } else if (live) {
-          rec = ld_stream_u4(a.ships + i); c = ld_stream_u32(a.clock + i); act = ld_stream_s16(a.actions + i);
-        }
-      }
+      const int tile = int(lds_u32(tile_b + st * 4u));
+      if (tile < 0) { more = false; break; }
+      const int i = tile * kThreads + tid;
+      const uint32_t so = st * uint32_t(sizeof(TileStage));
+      const uint4 rec = lds_u4(my_ship + so);
+      const uint32_t c = lds_u32(my_clock + so);
+      const int act = lds_s16(my_act + so);
       __syncwarp();
       if (lane == 0) mbar_arrive_s(empty_b + st * 8u);
       st = (st + 1u) & uint32_t(kStages - 1);
@@ -612,9 +627,9 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const uint32_t c1 = c + 1u;
       const bool do_reset = auto_reset && (no_fuel || (c1 & 0xFFFFu) >= trunc_at);
       const uint32_t ro = __umulhi(wd[2], P), rd = __umulhi(wd[3], P);                    // :232-233
-      const bool general = live && (!is_move || (in_map && (trigger || arrive || (do_reset && ro == rd))));
-      const bool ok = live && is_move && in_map && !general;
-      const bool off_map = live && is_move && !in_map;
+      const bool general = !is_move || (in_map && (trigger || arrive || (do_reset && ro == rd)));
+      const bool ok = is_move && in_map && !general;
+      const bool off_map = is_move && !in_map;
       {
         const double fuel1 = water ? __dsub_rn(fuel, cost) : fuel;                        // :298
         uint4 out;
@@ -633,20 +648,20 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
           st_stream_u4(a.ships + i, out);
           a.clock[i] = c_out;
         }
-        if (live && !general) a.io.reward_f32[i] = ok ? r : 0.f;
+        if (!general) a.io.reward_f32[i] = ok ? r : 0.f;
       }
       const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, ok && no_fuel);
       const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, ok && do_reset);
       const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, off_map);
       const uint32_t gen_w = __ballot_sync(0xFFFFFFFFu, general);
-      if (lane < 3 && i - lane < n) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
+      if (lane < 3) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
       if (gen_w) {
         if (general) defer[n_defer + __popc(gen_w & ((1u << lane) - 1u))] = i;
         n_defer += __popc(gen_w);
       }
     }
     // ------------------------------ drain the deferred envs, a warp-full at a time ------------------------------
-    if (n_defer == 0 && tile >= n_tiles) break;
+    if (n_defer == 0 && !more) break;
     __syncwarp();
     while (n_defer > 0) {
       const int k = min(n_defer, 32);
@@ -661,6 +676,15 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       n_defer -= k;
       __syncwarp();
     }
+  }
+  // the ragged last tile (n % 256 envs) never enters the pipeline: its owner CTA takes the general path for it
+  if (full_tiles * kThreads < n && int(blockIdx.x) == full_tiles % int(gridDim.x)) {
+    const int i = full_tiles * kThreads + tid;
+    const uint32_t f = i < n ? step_general_inline(a, smem, i) : 0u;
+    const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, f & kFlagDone);
+    const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, f & kFlagReset);
+    const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, f & kFlagError);
+    if (lane < 3 && i - lane < n) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
   }
 }
 

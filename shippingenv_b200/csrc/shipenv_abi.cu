@@ -63,6 +63,8 @@ struct shipenv_ctx {
   shipenv_consts consts = kDefaultConsts;
   // device blob
   void* d_world = nullptr;
+  uint32_t* d_tile_counter = nullptr;   // ticket counter of step_fast_kernel's tile scheduler
+  uint32_t tile_base = 0;
   std::vector<unsigned char> h_world;
   uint32_t world_bytes = 0;
   bool dirty = true;
@@ -195,6 +197,9 @@ int shipenv_ctx_create(int device, shipenv_ctx** out) {
   CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   cudaError_t e = cudaMalloc(&c->d_world, kMaxWorldBytes);
   if (e != cudaSuccess) { delete c; return fail(SHIPENV_E_CUDA, "cudaMalloc(world): %s", cudaGetErrorString(e)); }
+  e = cudaMalloc(&c->d_tile_counter, 256);
+  if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 256);
+  if (e != cudaSuccess) { cudaFree(c->d_world); delete c; return fail(SHIPENV_E_CUDA, "tile counter: %s", cudaGetErrorString(e)); }
   *out = c;
   return 0;
 }
@@ -204,6 +209,7 @@ int shipenv_ctx_destroy(shipenv_ctx* c) {
   {
     DeviceGuard guard(c->device);
     if (c->d_world) cudaFree(c->d_world);
+    if (c->d_tile_counter) cudaFree(c->d_tile_counter);
   }
   delete c;
   return 0;
@@ -314,6 +320,9 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
              c->P >= 2 && !c->no_fast_kernel) {
     const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes + kDeferCap * 4 * (kThreads / 32);
     if (int rc = grid_for(c, step_fast_kernel, c->occ_step_fast, kStepBlock, smem, tiles, &grid)) return rc;
+    a.tile_counter = c->d_tile_counter;
+    a.tile_base = c->tile_base;
+    c->tile_base += uint32_t(n / kThreads) + uint32_t(grid);   // every tile once + one failed ticket per CTA
     step_fast_kernel<<<grid, kStepBlock, smem, stream>>>(a);
   } else {
     const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes;
