@@ -165,6 +165,12 @@ int shipenv_sample_action(shipenv_ctx *ctx, const shipenv_ship *ships, const uin
  * as float32 rows [n, 6+4P] (the dtype the DQN feeds its network, agents/dqn.py:198). */
 int shipenv_observe(shipenv_ctx *ctx, const shipenv_ship *ships, float *obs, int64_t n, void *stream);
 
+/* DQNAgent.is_valid_action for every flat action (agents/dqn.py:125-175): moves always; SELECT_PORT k iff
+ * k != origin and the ship stands on port k; TAKE_CARGO / TAKE_FUEL v iff the ship is at a port (first
+ * match) and 0 < v <= that port's stock.  mask[i * words + a / 32] bit a % 32, words = ceil(A / 32),
+ * A = shipenv_num_actions (9 words for P = 5). */
+int shipenv_valid_actions(shipenv_ctx *ctx, const shipenv_ship *ships, uint32_t *mask, int64_t n, void *stream);
+
 /* MCTSAgent._rollout (agents/mcts.py:211-238) from copies of R root ships, S rollouts each,
  * at most L accepted steps.  Rollout (r, s) draws one continuous word stream from the cell
  * (seed ^ "ROLL"<<32, root_id_base + r, s).  returns[r*S+s] is the fp64 sum of step rewards;

@@ -104,6 +104,11 @@ class Oracle:
         lib().orc_observe(C.byref(self.w), _p(ships), _p(obs), C.c_int64(len(ships)))
         return obs
 
+    def valid_actions(self, ships):
+        valid = np.zeros((len(ships), 4 + self.P + 250), np.uint8)
+        lib().orc_valid_actions(C.byref(self.w), _p(ships), _p(valid), C.c_int64(len(ships)))
+        return valid
+
     def rollout(self, roots, S, L, seed, root_base=0):
         R = len(roots)
         ret = np.zeros((R, S), np.float64)

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "shipenv_sample_action": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]),
     "shipenv_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "shipenv_valid_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "shipenv_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "shipenv_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
@@ -193,6 +194,9 @@ class Context:
 
     def observe(self, ships, obs, n, stream):
         check(lib().shipenv_observe(self._h, ships, obs, n, stream))
+
+    def valid_actions(self, ships, mask, n, stream):
+        check(lib().shipenv_valid_actions(self._h, ships, mask, n, stream))
 
     def rollout(self, roots, R, S, L, returns, final, steps, status, seed, root_id_base, stream):
         check(lib().shipenv_rollout(self._h, roots, R, S, L, returns, final, steps, status, seed, root_id_base,

@@ -94,7 +94,7 @@ class BatchedEnvironment:
         self.done_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
         self.reset_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
         self.error_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
-        self._reward64 = self._status = self._taken = self._obs = None
+        self._reward64 = self._status = self._taken = self._obs = self._valid = None
         self.ep_return = self.stats = None
         if track_stats:
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -195,6 +195,19 @@ class BatchedEnvironment:
         obs = out if out is not None else self._buf("_obs", (self.n, self.obs_width), torch.float32)
         self.ctx.observe(self.ships.data_ptr(), obs.data_ptr(), self.n, self._stream())
         return obs
+
+    def valid_action_bits(self, out=None):
+        """``DQNAgent.is_valid_action`` for all actions of all envs: int32 [N, ceil(A/32)] bit words."""
+        words = (self.num_actions + 31) // 32
+        m = out if out is not None else self._buf("_valid", (self.n, words), torch.int32)
+        self.ctx.valid_actions(self.ships.data_ptr(), m.data_ptr(), self.n, self._stream())
+        return m
+
+    def valid_action_mask(self):
+        """The same as a bool tensor [N, A] (for ``q.masked_fill(~mask, -inf)``)."""
+        bits = self.valid_action_bits()
+        shifts = torch.arange(32, device=self.device, dtype=torch.int32)
+        return ((bits[:, :, None] >> shifts) & 1).reshape(self.n, -1)[:, :self.num_actions].bool()
 
     def sample_action(self, word0=0):
         """``Environment.sample_action`` per env -> (actions int16 [N], words_used uint8 [N], status uint8 [N])."""

@@ -780,6 +780,50 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const SampleArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// DQN valid-action mask (agents/dqn.py:125-175), one env per thread, ceil(A/32) words per env
+// ------------------------------------------------------------------------------------------
+struct ValidArgs {
+  const void* world; uint32_t world_bytes;
+  const uint4* ships; uint32_t* mask; int64_t n; int words;
+};
+
+// bits [lo, hi) of a bit string, restricted to word `wi`
+__device__ __forceinline__ uint32_t range_bits(int lo, int hi, int wi) {
+  const int a = max(lo - wi * 32, 0), b = min(hi - wi * 32, 32);
+  if (a >= b) return 0u;
+  return (b == 32 ? 0xFFFFFFFFu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
+}
+
+__global__ void __launch_bounds__(kThreads) valid_actions_kernel(const ValidArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t world_bar;
+  stage_world(smem, a.world, a.world_bytes, &world_bar);
+  const WorldView w(smem);
+  const int P = w.h->P;
+  const int64_t n_tiles = (a.n + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i = tile * kThreads + threadIdx.x;
+    if (i >= a.n) continue;
+    const ShipR s = unpack(a.ships[i]);
+    const uint32_t key = uint32_t(s.x) | (uint32_t(s.y) << 8);
+    uint32_t select = 0;                              // bit k: port k selectable (:141-156)
+    for (int k = 0; k < P; ++k)
+      if (k != s.origin && (w.h->port[k] & 0xFFFFu) == key) select |= 1u << k;
+    const int cur = current_port(w, s);                // :159-173
+    const int n_cargo = cur >= 0 ? min(int(w.h->port[cur] >> 24), SHIPENV_N_CARGO_ACTIONS - 1) : 0;
+    const int n_fuel = cur >= 0 ? min(int((w.h->port[cur] >> 16) & 255u), SHIPENV_N_FUEL_ACTIONS - 1) : 0;
+    const int c0 = 4 + P + 1, f0 = 4 + P + SHIPENV_N_CARGO_ACTIONS + 1;   // first amount is 1
+    for (int wi = 0; wi < a.words; ++wi) {
+      uint32_t m = range_bits(0, 4, wi);               // the four moves are always valid (:137-139)
+      m |= range_bits(c0, c0 + n_cargo, wi) | range_bits(f0, f0 + n_fuel, wi);
+      for (int k = 0; k < P; ++k)
+        if ((select >> k) & 1u) m |= range_bits(4 + k, 5 + k, wi);
+      a.mask[i * a.words + wi] = m;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // MCTS rollouts: the whole simulations x max_rollout_steps loop in one kernel
 // ------------------------------------------------------------------------------------------
 struct RolloutArgs {

@@ -71,7 +71,7 @@ struct shipenv_ctx {
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_step_fast, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout;
+  Occ occ_step_fast, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid;
 };
 
 namespace {
@@ -372,6 +372,25 @@ int shipenv_observe(shipenv_ctx* c, const shipenv_ship* ships, float* obs, int64
   int grid = 0;
   if (int rc = grid_for(c, observe_kernel, c->occ_observe, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
   observe_kernel<<<grid, kThreads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int shipenv_valid_actions(shipenv_ctx* c, const shipenv_ship* ships, uint32_t* mask, int64_t n, void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (n < 0 || (n > 0 && (!ships || !mask))) return fail(SHIPENV_E_ARG, "valid_actions: null buffer or negative n");
+  if (n == 0) return 0;
+  if (c->P < 0) return fail(SHIPENV_E_STATE, "no port table set (shipenv_set_ports)");
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  const int A = 4 + c->P + SHIPENV_N_CARGO_ACTIONS + SHIPENV_N_FUEL_ACTIONS;
+  ValidArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(ships), mask, n, (A + 31) / 32};
+  const size_t smem = c->world_bytes;
+  int grid = 0;
+  if (int rc = grid_for(c, valid_actions_kernel, c->occ_valid, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
+  valid_actions_kernel<<<grid, kThreads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   ++g_launches;
   return 0;

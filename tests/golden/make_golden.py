@@ -93,9 +93,45 @@ def save(name, **arrays):
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def valid_action_golden(ns):
+    """g9: the reference's DQNAgent.is_valid_action (agents/dqn.py:125-175) over all 259 actions."""
+    import agents.dqn as dqn
+    PORTS = ns.consts.DEFAULT_PORTS
+    b = RefBatch(ns, 64, SEED, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.reset()
+    agent = dqn.DQNAgent.__new__(dqn.DQNAgent)
+    pos, cargo, fuel, valid = [], [], [], []
+
+    def snapshot():
+        p, c, f = b.states()
+        pos.append(p); cargo.append(c); fuel.append(f)
+        rows = []
+        for e in b.envs:
+            agent.env = e
+            rows.append([agent.is_valid_action(a) for a in range(259)])
+        valid.append(np.array(rows, np.uint8))
+
+    snapshot()                                        # right after reset: on the origin port
+    for t in range(40):
+        b.step(np.full(64, POLICY), 0, False)
+        if t in (0, 1, 5, 39):
+            snapshot()
+    # crafted: ship on a port that is not its origin / origin None / on the destination port
+    for i, (x, y, o, d) in enumerate([(60, 22, 4, 1), (60, 22, NONE_PORT, NONE_PORT), (41, 40, 0, 3), (78, 29, 1, 2)]):
+        b.set_state(i, x, y, o, d, 3, 150.5)
+    snapshot()
+    save("g9_valid_actions", pos=np.concatenate(pos), cargo=np.concatenate(cargo), fuel=np.concatenate(fuel),
+         valid=np.concatenate(valid), **port_meta(b))
+    print("  valid-action rows:", sum(len(v) for v in valid), " mean valid per row:",
+          float(np.concatenate(valid).sum(1).mean()))
+
+
 def main():
     ns = import_reference()
     PORTS = ns.consts.DEFAULT_PORTS
+    if "valid" in sys.argv[1:]:
+        valid_action_golden(ns)
+        return
 
     # --- self-check: the reference imported here is the program SURVEY App. C hashed ----
     ns.envmod.random = stock_random
@@ -283,6 +319,8 @@ def main():
     out["root_id_base"] = np.uint64(1000)
     out["seed"] = np.uint64(SEED)
     save("g8_rollouts", **out, **port_meta(b))
+
+    valid_action_golden(ns)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,26 @@
+"""GPU: the consumers of the path that BASELINE configs 4 and 5 name run end to end on the device."""
+import importlib.util
+import math
+import os
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "examples", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("envs,steps", [(1, 300), (512, 60)])
+def test_dqn_loop_on_device(envs, steps):
+    out = _load("dqn_device").train(envs=envs, steps=steps, max_steps=50)
+    assert out["agent_steps_per_s"] > 0 and out["final_epsilon"] < 1.0
+    assert all(math.isfinite(v) for v in out["loss_first_last"])
+    if envs > 1:
+        assert out["episodes"]["total_episodes"] > 0

@@ -226,3 +226,76 @@ def test_cuda_episode_statistics(torch_cuda, default_map):
     assert s["max_reward"] == max(rets) and s["min_reward"] == min(rets)
     assert np.allclose(env.ep_return.cpu().numpy(), ep, rtol=0, atol=1e-12)
     assert env.state_numpy()[0].tobytes() == ships.tobytes()
+
+
+def test_cuda_full_size_properties(torch_cuda, default_map):
+    """BASELINE config 3 size (2,097,152 envs per GPU): properties that do not need the oracle.
+    (a) sharding invariance: one launch over all envs == four launches over contiguous quarters with the
+        matching env_id_base (what ranks do), bit for bit, through fast and general kernels alike;
+    (b) invariants of the transition: ships stay on passable cells inside the map, the clock advances by one
+        per accepted step or jumps to the next episode, rejected envs are untouched, a reset puts the ship on
+        its origin port with full fuel, fuel never increases under MOVE actions without a reset."""
+    torch = torch_cuda
+    from shippingenv_b200 import BatchedEnvironment, unpack_bits
+    n, seed, T = 1 << 21, 0x5EED, 24
+    passable = default_map["passable"]
+    whole = BatchedEnvironment(n, passable=passable, seed=seed, device="cuda:0", max_steps=17)
+    q = n // 4
+    parts = [BatchedEnvironment(q, passable=passable, seed=seed, device="cuda:0", max_steps=17, env_id_base=k * q)
+             for k in range(4)]
+    whole.reset()
+    for p in parts:
+        p.reset()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    pas = torch.from_numpy(passable.astype(np.bool_)).cuda()
+    ports = torch.tensor(whole.ports, device="cuda")
+    for t in range(T):
+        a = torch.randint(0, 4, (n,), generator=gen, device="cuda", dtype=torch.int16)
+        if t % 5 == 4:
+            a = torch.randint(-1, 259, (n,), generator=gen, device="cuda", dtype=torch.int16)
+        before_ships, before_clock = whole.ships.clone(), whole.clock.clone()
+        r = whole.step(a, want_status=(t % 2 == 0))          # alternate general / fast kernel
+        for k, p in enumerate(parts):
+            p.step(a[k * q:(k + 1) * q].contiguous(), want_status=(t % 2 == 1))
+        assert torch.equal(whole.ships, torch.cat([p.ships for p in parts])), f"split differs at step {t}"
+        assert torch.equal(whole.clock, torch.cat([p.clock for p in parts]))
+        assert torch.equal(whole.reward, torch.cat([p.reward for p in parts]))
+        assert torch.equal(whole.done_bits, torch.cat([p.done_bits for p in parts]))
+        assert torch.equal(whole.reset_bits, torch.cat([p.reset_bits for p in parts]))
+        err = unpack_bits(r.error_bits, n)
+        rst = unpack_bits(r.reset_bits, n)
+        x, y = whole.x.long(), whole.y.long()
+        assert bool((x < 100).all()) and bool((y < 100).all()) and bool(pas[x, y].all())
+        assert torch.equal(whole.ships[err], before_ships[err]) and torch.equal(whole.clock[err], before_clock[err])
+        ok = ~err & ~rst
+        assert bool((whole.clock[ok] == before_clock[ok] + 1).all())
+        assert bool((whole.clock[rst] & 0xFFFF == 0).all())
+        assert bool(((whole.clock[rst] >> 16) == (before_clock[rst] >> 16) + 1).all())
+        o = whole.origin.long()[rst]
+        assert bool((whole.fuel[rst] == 200.0).all()) and bool((whole.cargo[rst] == 0).all())
+        assert torch.equal(torch.stack([x[rst], y[rst]], 1), ports[o])
+        if t % 5 != 4:
+            fuel_before = before_ships.view(torch.float64)[:, 1]
+            assert bool((whole.fuel[ok] <= fuel_before[ok]).all())
+        assert bool((whole.reward[err] == 0).all())
+
+
+def test_cuda_valid_action_mask(torch_cuda, default_map):
+    """The DQN valid-action mask on device == DQNAgent.is_valid_action of the reference (fixture g9) and ==
+    the oracle on a larger seeded population."""
+    from shippingenv_b200 import BatchedEnvironment
+    z = golden("g9_valid_actions")
+    n = len(z["cargo"])
+    env = BatchedEnvironment(n, passable=z["passable"], device="cuda:0")
+    env.load_state(orc.ships_from(z["pos"], z["cargo"], z["fuel"]))
+    mask = env.valid_action_mask().cpu().numpy()
+    assert mask.shape == (n, 259) and (mask == z["valid"].astype(bool)).all()
+    n = 20_000
+    env = BatchedEnvironment(n, passable=default_map["passable"], seed=3, device="cuda:0", max_steps=30)
+    env.reset()
+    o = orc.Oracle(default_map["passable"], env.ports, env.port_fuel, env.port_cargo)
+    for t in range(12):
+        env.step_policy()
+        ships, _ = env.state_numpy()
+        want = o.valid_actions(ships.view(orc.SHIP_DTYPE).reshape(-1))
+        assert (env.valid_action_mask().cpu().numpy() == want.astype(bool)).all(), t
