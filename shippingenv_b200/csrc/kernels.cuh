@@ -530,6 +530,10 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
     mbar_expect_tx(&world_bar, a.world_bytes);
     tma_load_bulk(smem, a.world, a.world_bytes, &world_bar);
   }
+  // Programmatic dependent launch: let the next step's grid start its prologue while this one runs, and
+  // do not touch ships / clock / tickets before the previous grid has completed and flushed its stores.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid >= kThreads) {             // ---- producer warp: lane 0 streams tiles in with TMA ----
     if (tid == kThreads) {
       // Tiles are handed out by a global ticket counter, so SMs that run ahead simply take more tiles

@@ -323,7 +323,13 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
     a.tile_counter = c->d_tile_counter;
     a.tile_base = c->tile_base;
     c->tile_base += uint32_t(n / kThreads) + uint32_t(grid);   // every tile once + one failed ticket per CTA
-    step_fast_kernel<<<grid, kStepBlock, smem, stream>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStepBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this grid's prologue
+    attr[0].val.programmaticStreamSerializationAllowed = 1;            // with the previous grid's tail
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, step_fast_kernel, a));
   } else {
     const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes;
     if (lean) {
