@@ -9,8 +9,8 @@ per launch per GPU (16M over 8), default map, 5 default ports, uniform random mo
 done or after 1,000 steps, Philox seed 0x5EED, global env ids rank * 2^21 + i (weak scaling, no
 collective on the step path).  One "step" = one shipenv_step launch over every env of the rank.
 
-Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM and L2
-flushed between steps; `e2e` goes through the same C-ABI call with the step's actions coming
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM (4 env groups
+per GPU stepped round-robin so that the working set exceeds L2); `e2e` goes through the same C-ABI call with the step's actions coming
 from pinned host memory and reward + done/reset masks going back to it, copies inside the timed
 region.  `--impl reference` times the CPU oracle port (oracle/shipenv_oracle.c, the reference
 is pure Python and cannot travel to the GPU box) on all host cores on the same workload.
@@ -303,6 +303,37 @@ def run_ours(args):
     e2e_ms = max(t0.elapsed_time(e) for e in ends)
     checksum = float(sum(float(h.sum()) for h in h_reward))
 
+    # ---- the other device paths of the scope table, N = 1 only, a few launches each (reported as extras) ----
+    extras = {}
+    if world_size == 1 and not args.no_extras:
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps
+        g0 = envs[0]
+        ms = timed(lambda: g0.step_policy(), 50)
+        extras["policy_step"] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_launch": ms,
+                                 "what": "action -1: on-device sample_action + retry (Environment.sample_action loop)"}
+        ms = timed(lambda: g0.step(pool[0], want_obs=True), 50)
+        extras["step_with_observation"] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_launch": ms,
+                                           "bytes_per_env_step": 150, "hbm_gbs": n * 150 / (ms * 1e-3) / 1e9,
+                                           "what": "fused preprocess_state rows, f32 [n, 26], TMA bulk stores"}
+        ms = timed(lambda: g0.valid_action_bits(), 50)
+        extras["valid_action_mask"] = {"envs_per_s": n / (ms * 1e-3), "ms_per_launch": ms}
+        R, S, L = 65536, 50, 100                      # BASELINE configs[3]
+        roots = g0.ships[:R].contiguous()
+        holder = {}
+        ms = timed(lambda: holder.update(out=g0.rollout(S, L, roots=roots)), 5)
+        rsteps = int(holder["out"]["steps"].sum().item())
+        extras["mcts_rollouts"] = {"roots": R, "simulations": S, "max_rollout_steps": L, "ms_per_launch": ms,
+                                   "rollout_steps_per_s": rsteps / (ms * 1e-3), "roots_per_s": R / (ms * 1e-3),
+                                   "what": "MCTSAgent._rollout x 50 per root in one kernel (reference: 5.6 roots/s/core)"}
+
     # ---- max over ranks ----
     times = torch.tensor([total_ms, flushed_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
@@ -340,6 +371,8 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks.summary(),
             "rejected_actions_last_step": err, "reward_checksum": checksum,
         }
+        if extras:
+            line["extras"] = extras
         if world_size == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             v, s, dt = cpu_steps_per_s(1 << 18, args.cpu_seconds, threads)
@@ -364,6 +397,7 @@ def main():
     ap.add_argument("--groups", type=int, default=GROUPS, help="env groups per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     import __graft_entry__ as entry
