@@ -188,21 +188,6 @@ struct StepArgs {
   uint32_t tile_base;       // ticket value this launch starts at
 };
 
-// Philox4x32-10 with the round keys precomputed on the host: 20 IMAD.WIDE + 20 LOP3.
-__device__ __forceinline__ void philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                          const uint32_t (&rk)[20], uint32_t (&out)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t h0 = __umulhi(kPhiloxM0, c0), l0 = kPhiloxM0 * c0;
-    const uint32_t h1 = __umulhi(kPhiloxM1, c2), l1 = kPhiloxM1 * c2;
-    c0 = h1 ^ c1 ^ rk[2 * r];
-    c2 = h0 ^ c3 ^ rk[2 * r + 1];
-    c1 = l1;
-    c3 = l0;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 // Observation row head (utils/preprocessing.py:53-60): x, y, fuel, "cargo" (= fuel, the
 // state dict copies it, shipping/environment.py:206), origin | -1, dest | -1.
 __device__ __forceinline__ void obs_head(const ShipR& s, float* row) {
@@ -246,7 +231,7 @@ __device__ __forceinline__ uint32_t step_general_inline(const StepArgs& a, const
   const int act = a.actions[i];
   ShipR s = unpack(rec);
   Rng g;
-  g.seek(a.seed, 0u, c, a.env_id_base + uint64_t(uint32_t(i)), a.word0);
+  g.seek(a.round_key, c, a.env_id_base + uint64_t(uint32_t(i)), a.word0);
   double reward = 0.0;
   bool done = false;
   int taken = act, status;
@@ -699,9 +684,10 @@ struct ResetArgs {
   const void* world; uint32_t world_bytes;
   uint4* ships; uint32_t* clock; const uint32_t* mask_bits;
   uint64_t seed, env_id_base; int64_t n;
+  uint32_t round_key[20];
 };
 
-__global__ void __launch_bounds__(kThreads) reset_kernel(const ResetArgs a) {
+__global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__ ResetArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
@@ -714,7 +700,7 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const ResetArgs a) {
     const uint32_t c = a.clock[i];
     ShipR s;
     Rng g;
-    g.seek(a.seed, 0u, c, a.env_id_base + uint64_t(i), 0u);
+    g.seek(a.round_key, c, a.env_id_base + uint64_t(i), 0u);
     env_reset(w, s, g);
     st_stream_u4(a.ships + i, pack(s));
     a.clock[i] = ((c >> 16) + 1u) << 16;
@@ -761,9 +747,10 @@ struct SampleArgs {
   const uint4* ships; const uint32_t* clock;
   int16_t* actions; uint8_t* words_used; uint8_t* status;
   uint64_t seed, env_id_base; int64_t n; uint32_t word0;
+  uint32_t round_key[20];
 };
 
-__global__ void __launch_bounds__(kThreads) sample_kernel(const SampleArgs a) {
+__global__ void __launch_bounds__(kThreads) sample_kernel(const __grid_constant__ SampleArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
@@ -774,7 +761,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const SampleArgs a) {
     if (i >= a.n) continue;
     const ShipR s = unpack(a.ships[i]);
     Rng g;
-    g.seek(a.seed, 0u, a.clock[i], a.env_id_base + uint64_t(i), a.word0);
+    g.seek(a.round_key, a.clock[i], a.env_id_base + uint64_t(i), a.word0);
     int cat = kCatJunk, val = 0;
     int st = w.h->P == 0 ? SHIPENV_ST_NO_PORTS : sample_action(w, s, g, cat, val);
     a.actions[i] = st == SHIPENV_ST_OK ? int16_t(encode_action(cat, val, w.h->P)) : int16_t(-2);
@@ -835,11 +822,12 @@ struct RolloutArgs {
   const uint4* roots; int64_t R; int S, L;
   double* returns; uint4* final; int32_t* steps; uint8_t* status;
   uint64_t seed, root_id_base;
+  uint32_t round_key[20];   // of the rollout key: seed with k1 ^= "ROLL"
 };
 
 constexpr int kRolloutThreads = 128;
 
-__global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const RolloutArgs a) {
+__global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_constant__ RolloutArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
@@ -853,7 +841,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const RolloutA
     const int sim = int(j - r * a.S);
     ShipR s = unpack(__ldg(a.roots + r));
     Rng g;
-    g.seek(a.seed, kRolloutTweak, uint32_t(sim), a.root_id_base + uint64_t(r), 0u);
+    g.seek(a.round_key, uint32_t(sim), a.root_id_base + uint64_t(r), 0u);
     double total_reward = 0.0;                     // agents/mcts.py:224
     bool done = false;
     int steps = 0, st = SHIPENV_ST_OK, fails = 0;

@@ -39,20 +39,39 @@ __device__ __forceinline__ double unit_double(uint32_t w) {
   return __dadd_rn(__hiloint2double(0x41300000, int(w)), -1048576.0);
 }
 
+// Philox4x32-10 with the ten round keys (k0 + r*W0, k1 + r*W1) precomputed on the host and passed in the
+// kernel parameters: 20 IMAD.WIDE + 20 LOP3 with the keys as constant-bank operands.
+__device__ __forceinline__ void philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                          const uint32_t* __restrict__ rk, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(kPhiloxM0, c0), l0 = kPhiloxM0 * c0;
+    const uint32_t h1 = __umulhi(kPhiloxM1, c2), l1 = kPhiloxM1 * c2;
+    c0 = h1 ^ c1 ^ rk[2 * r];
+    c2 = h0 ^ c3 ^ rk[2 * r + 1];
+    c1 = l1;
+    c3 = l0;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 struct Rng {
-  uint32_t c1, c2, c3, k0, k1;
+  const uint32_t* rk;  // round keys of the stream's key (kernel parameter space)
+  uint32_t c1, c2, c3;
   uint32_t i;        // next word of the cell
   uint32_t blk;      // index of the cached block (i >> 2), ~0u = none
   uint32_t w[4];
 
-  __device__ __forceinline__ void seek(uint64_t seed, uint32_t tweak, uint32_t cell1, uint64_t id, uint32_t word) {
+  __device__ __forceinline__ void seek(const uint32_t* round_keys, uint32_t cell1, uint64_t id, uint32_t word) {
+    rk = round_keys;
     c1 = cell1; c2 = uint32_t(id); c3 = uint32_t(id >> 32);
-    k0 = uint32_t(seed); k1 = uint32_t(seed >> 32) ^ tweak;
     i = word; blk = ~0u;
   }
   __device__ __forceinline__ uint32_t next() {
     const uint32_t b = i >> 2;
-    if (b != blk) { philox4x32_10(b, c1, c2, c3, k0, k1, w); blk = b; }
+    // key schedule on the fly here: with many inlined call sites, reloading ten round keys per site costs
+    // more than the 18 adds (measured on the rollout kernel); the streaming kernel uses philox_rk directly
+    if (b != blk) { philox4x32_10(b, c1, c2, c3, rk[0], rk[1], w); blk = b; }
     const uint32_t s = i & 3u;
     ++i;
     return s == 0 ? w[0] : s == 1 ? w[1] : s == 2 ? w[2] : w[3];

@@ -84,7 +84,7 @@ int build_world(shipenv_ctx* c) {
   if (c->P < 0) return fail(SHIPENV_E_STATE, "no port table set (shipenv_set_ports)");
   const int wpr = (c->H + 31) / 32;
   const size_t n_words = size_t(c->W) * wpr;
-  const size_t bytes = (sizeof(WorldHdr) + n_words * 4 + 15) & ~size_t(15);
+  const size_t bytes = (sizeof(WorldHdr) + 2 * n_words * 4 + 15) & ~size_t(15);
   c->h_world.assign(bytes, 0);
   WorldHdr* h = new (c->h_world.data()) WorldHdr();
   uint32_t* bits = reinterpret_cast<uint32_t*>(c->h_world.data() + sizeof(WorldHdr));
@@ -120,7 +120,11 @@ int build_world(shipenv_ctx* c) {
       if (c->passable[size_t(x) * c->H + y]) bits[size_t(x) * wpr + (y >> 5)] |= 1u << (y & 31);
   // a port cell is passable whatever the map says (add_port stamps Entity.PORT, :65)
   for (int p = 0; p < c->P; ++p)
-    if (c->px[p] < c->W && c->py[p] < c->H) bits[size_t(c->px[p]) * wpr + (c->py[p] >> 5)] |= 1u << (c->py[p] & 31);
+    if (c->px[p] < c->W && c->py[p] < c->H) {
+      const size_t word = size_t(c->px[p]) * wpr + (c->py[p] >> 5);
+      bits[word] |= 1u << (c->py[p] & 31);
+      bits[n_words + word] |= 1u << (c->py[p] & 31);     // second bitmap: port cells
+    }
   c->world_bytes = uint32_t(bytes);
   return 0;
 }
@@ -151,6 +155,14 @@ int grid_for(shipenv_ctx* c, Kernel kernel, shipenv_ctx::Occ& occ, int threads, 
   *grid = int(tiles < resident ? tiles : resident);
   if (*grid < 1) *grid = 1;
   return 0;
+}
+
+// (k0 + r*W0, k1 + r*W1), r = 0..9, for key = seed with k1 ^= tweak
+void fill_round_keys(uint32_t* rk, uint64_t seed, uint32_t tweak) {
+  for (int r = 0; r < 10; ++r) {
+    rk[2 * r] = uint32_t(seed) + uint32_t(r) * kPhiloxW0;
+    rk[2 * r + 1] = (uint32_t(seed >> 32) ^ tweak) + uint32_t(r) * kPhiloxW1;
+  }
 }
 
 int check_ctx(shipenv_ctx* c) {
@@ -266,7 +278,8 @@ int shipenv_reset(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, uint64_t
   DeviceGuard guard(c->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = sync_world(c, stream)) return rc;
-  ResetArgs a{c->d_world, c->world_bytes, reinterpret_cast<uint4*>(ships), clock, mask_bits, seed, env_id_base, n};
+  ResetArgs a{c->d_world, c->world_bytes, reinterpret_cast<uint4*>(ships), clock, mask_bits, seed, env_id_base, n, {}};
+  fill_round_keys(a.round_key, seed, 0u);
   const size_t smem = c->world_bytes;
   int grid = 0;
   if (int rc = grid_for(c, reset_kernel, c->occ_reset, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
@@ -296,10 +309,7 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   if (io) a.io = *io; else memset(&a.io, 0, sizeof(a.io));
   a.seed = seed; a.env_id_base = env_id_base; a.n = n; a.max_steps = max_steps; a.flags = flags; a.word0 = word0;
   a.obs_width = 6 + 4 * c->P;
-  for (int r = 0; r < 10; ++r) {
-    a.round_key[2 * r] = uint32_t(seed) + uint32_t(r) * kPhiloxW0;
-    a.round_key[2 * r + 1] = uint32_t(seed >> 32) + uint32_t(r) * kPhiloxW1;
-  }
+  fill_round_keys(a.round_key, seed, 0u);
   const int64_t tiles = (n + kThreads - 1) / kThreads;
   const bool lean = !a.io.reward_f64 && !a.io.status && !a.io.taken && !a.io.ep_return;
   int grid = 0;
@@ -355,7 +365,8 @@ int shipenv_sample_action(shipenv_ctx* c, const shipenv_ship* ships, const uint3
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = sync_world(c, stream)) return rc;
   SampleArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(ships), clock, actions_out, words_used,
-               status, seed, env_id_base, n, word0};
+               status, seed, env_id_base, n, word0, {}};
+  fill_round_keys(a.round_key, seed, 0u);
   const size_t smem = c->world_bytes;
   int grid = 0;
   if (int rc = grid_for(c, sample_kernel, c->occ_sample, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
@@ -413,7 +424,8 @@ int shipenv_rollout(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = sync_world(c, stream)) return rc;
   RolloutArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, returns,
-                reinterpret_cast<uint4*>(final), steps, status, seed, root_id_base};
+                reinterpret_cast<uint4*>(final), steps, status, seed, root_id_base, {}};
+  fill_round_keys(a.round_key, seed, kRolloutTweak);
   const size_t smem = c->world_bytes;
   const int64_t tiles = (R * int64_t(S) + kRolloutThreads - 1) / kRolloutThreads;
   int grid = 0;

@@ -35,6 +35,7 @@ __device__ __forceinline__ uint4 pack(const ShipR& s) {
 
 // _get_current_port_idx (:145-153): first port at the ship's position, -1 if none.
 __device__ __forceinline__ int current_port(const WorldView& w, const ShipR& s) {
+  if (unsigned(s.x) >= unsigned(w.h->W) || unsigned(s.y) >= unsigned(w.h->H) || !w.port_cell(s.x, s.y)) return -1;
   const uint32_t key = uint32_t(s.x) | (uint32_t(s.y) << 8);
   int found = -1;
   for (int k = w.h->P - 1; k >= 0; --k)

@@ -15,7 +15,8 @@ constexpr int kMaxCap = SHIPENV_MAX_CAPACITY + 1;
 constexpr int kNone = SHIPENV_NONE_PORT;
 constexpr int kMaxTries = SHIPENV_MAX_TRIES;
 
-// Fixed-size header followed by W*wpr bitmap words (bit y&31 of word x*wpr + (y>>5)).
+// Fixed-size header followed by two W*wpr-word bitmaps (bit y&31 of word x*wpr + (y>>5)): passable cells,
+// then cells that hold a port (so that "is the ship at a port?" is one shared-memory load, not a scan).
 struct alignas(16) WorldHdr {
   int32_t W, H, P, wpr;          // wpr = ceil(H / 32)
   int32_t cargo0, capacity;      // Initial.CARGO, Initial.MAX_CARGO_CAPACITY
@@ -35,7 +36,7 @@ struct alignas(16) WorldHdr {
 };
 static_assert(sizeof(WorldHdr) % 16 == 0, "world header must stay 16-byte sized for the bulk copy");
 
-constexpr size_t kMaxWorldBytes = sizeof(WorldHdr) + size_t(kMaxDim) * (kMaxDim / 32) * 4;
+constexpr size_t kMaxWorldBytes = sizeof(WorldHdr) + 2 * size_t(kMaxDim) * (kMaxDim / 32) * 4;
 
 // View over a staged world (shared or global memory).
 struct WorldView {
@@ -46,6 +47,9 @@ struct WorldView {
         bits(reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(base) + sizeof(WorldHdr))) {}
   __device__ __forceinline__ bool passable(int x, int y) const {
     return (bits[x * h->wpr + (y >> 5)] >> (y & 31)) & 1u;
+  }
+  __device__ __forceinline__ bool port_cell(int x, int y) const {
+    return (bits[h->n_bit_words + x * h->wpr + (y >> 5)] >> (y & 31)) & 1u;
   }
 };
 
