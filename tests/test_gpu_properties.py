@@ -1,0 +1,91 @@
+"""GPU: hypothesis-driven edge coverage -- arbitrary ship records (including states no trajectory reaches),
+arbitrary int16 actions, clocks near the 16-bit step boundary, all kernel variants -- CUDA vs the oracle."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from conftest import golden
+from oracle import lib as orc
+
+pytestmark = pytest.mark.gpu
+
+FUEL_EDGES = np.array([0.0, -0.0, 0.5, 0.9, 0.95, 1.0, 1.05, 1.1, 1.1000000000000001, 200.0, -3.5, 1e-300, 1e6,
+                       0.8999999999999999, 5e-324, 1e15], np.float64)
+ACTION_EDGES = np.array([-1, -1, -1, 0, 1, 2, 3, 4, 8, 9, 10, 29, 58, 59, 60, 75, 258, 259, 260, -2, -32768, 32767,
+                         0x4000, 0x4001, 0x4014, 0x5FFF, 0x6000, 0x6001, 0x6010, 0x7FFF, 0x3FFF], np.int64)
+
+
+def random_population(rng, n, passable, ports):
+    s = np.zeros(n, orc.SHIP_DTYPE)
+    on_port = rng.random(n) < 0.35
+    k = rng.integers(0, len(ports), n)
+    s["x"] = np.where(on_port, np.array(ports)[k, 0], rng.integers(0, 100, n))
+    s["y"] = np.where(on_port, np.array(ports)[k, 1], rng.integers(0, 100, n))
+    edge = rng.random(n) < 0.15                       # hug the map border so that off-map moves occur
+    s["x"] = np.where(edge, rng.choice([0, 99], n), s["x"])
+    s["origin"] = rng.choice([0, 1, 2, 3, 4, 255], n)
+    s["dest"] = rng.choice([0, 1, 2, 3, 4, 255], n, p=[.18, .18, .18, .18, .18, .1])
+    s["cargo"] = rng.choice([0, 0, 1, 2, 7, 25, 49, 50, 51, 60, 1000, 2_000_000, -1, -7], n)
+    fuel = rng.random(n) * 210 - 5
+    use_edge = rng.random(n) < 0.4
+    s["fuel"] = np.where(use_edge, rng.choice(FUEL_EDGES, n), fuel)
+    clock = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    near = rng.random(n) < 0.5                        # step counters around max_steps and the 16-bit wrap
+    clock = np.where(near, (clock & np.uint32(0xFFFF0000)) | rng.choice([0, 1, 35, 36, 37, 65534, 65535], n).astype(np.uint32), clock)
+    return s, clock.astype(np.uint32)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2**63 - 1), n=st.sampled_from([1, 31, 32, 33, 255, 256, 257, 1000, 4099]),
+       max_steps=st.sampled_from([0, 1, 37, 65535]), auto_reset=st.booleans(), lean=st.booleans(),
+       base=st.sampled_from([0, 7, (1 << 32) - 3, (1 << 40) + 11]), word0=st.sampled_from([0, 0, 1, 5]))
+def test_one_step_from_arbitrary_states(seed, n, max_steps, auto_reset, lean, base, word0):
+    import torch
+    from shippingenv_b200 import BatchedEnvironment, unpack_bits
+    z = golden("default_map")
+    rng = np.random.default_rng(seed % (1 << 32))
+    env = BatchedEnvironment(n, passable=z["passable"], seed=seed, device="cuda:0", env_id_base=base,
+                             max_steps=max_steps, auto_reset=auto_reset)
+    o = orc.Oracle(z["passable"], env.ports, env.port_fuel, env.port_cargo)
+    ships, clock = random_population(rng, n, z["passable"], env.ports)
+    acts = np.where(rng.random(n) < 0.5, rng.integers(0, 4, n), rng.choice(ACTION_EDGES, n)).astype(np.int16)
+    env.load_state(ships, clock)
+    a = torch.from_numpy(acts).cuda()
+    if lean:
+        r = env.step(a, word0=word0)                                   # fast kernel when word0 == 0
+    else:
+        r = env.step(a, want_status=True, want_taken=True, want_reward64=True, want_obs=True, word0=word0)
+    ref = o.step(ships, clock, acts, seed, base, max_steps, auto_reset, word0)
+    g_ships, g_clock = env.state_numpy()
+    bad = np.nonzero((g_ships != ships.view(np.uint8).reshape(n, 16)).any(1))[0]
+    assert bad.size == 0, (bad[:5], acts[bad[:5]], g_ships[bad[:5]], ships[bad[:5]])
+    assert (g_clock == clock).all()
+    assert (r.reward.cpu().numpy() == ref["reward"].astype(np.float32)).all()
+    assert (unpack_bits(r.done_bits, n).cpu().numpy() == ref["done"].astype(bool)).all()
+    assert (unpack_bits(r.reset_bits, n).cpu().numpy() == ref["reset"].astype(bool)).all()
+    assert (unpack_bits(r.error_bits, n).cpu().numpy() == (ref["status"] != 0)).all()
+    if not lean:
+        assert (r.status.cpu().numpy() == ref["status"]).all()
+        assert (r.reward64.cpu().numpy().view(np.uint64) == ref["reward"].view(np.uint64)).all()
+        ok = ref["status"] == 0
+        assert (r.taken.cpu().numpy()[ok] == ref["taken"][ok]).all()
+        assert (r.obs.cpu().numpy().view(np.uint32) == o.observe(ships).view(np.uint32)).all()
+
+
+@settings(max_examples=8, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2**63 - 1), S=st.sampled_from([1, 3, 50]), L=st.sampled_from([0, 1, 17, 100]))
+def test_rollouts_from_arbitrary_roots(seed, S, L):
+    from shippingenv_b200 import BatchedEnvironment
+    z = golden("default_map")
+    rng = np.random.default_rng(seed % (1 << 32))
+    R = 300
+    env = BatchedEnvironment(R, passable=z["passable"], seed=seed, device="cuda:0")
+    o = orc.Oracle(z["passable"], env.ports, env.port_fuel, env.port_cargo)
+    roots, _ = random_population(rng, R, z["passable"], env.ports)
+    env.load_state(roots)
+    out = env.rollout(S, L, root_id_base=seed & 0xFFFF, want_final=True)
+    want, fin, steps, status = o.rollout(roots, S, L, seed, seed & 0xFFFF)
+    assert (out["status"].cpu().numpy() == status).all()
+    assert (out["steps"].cpu().numpy() == steps).all()
+    assert (out["returns"].cpu().numpy().view(np.uint64) == want.view(np.uint64)).all()
+    assert out["final"].cpu().numpy().tobytes() == fin.tobytes()
