@@ -171,6 +171,12 @@ int shipenv_observe(shipenv_ctx *ctx, const shipenv_ship *ships, float *obs, int
  * A = shipenv_num_actions (9 words for P = 5). */
 int shipenv_valid_actions(shipenv_ctx *ctx, const shipenv_ship *ships, uint32_t *mask, int64_t n, void *stream);
 
+/* discretize_state (utils/preprocessing.py:65-90), the key of the tabular agents (agents/sarsa.py:148,187-188):
+ * keys[i] = {x, y, min(int("cargo" / 10), 4), min(int(fuel / 20), 4), origin | -1, dest | -1} as int16[6],
+ * where "cargo" is the state dict's copy of fuel (shipping/environment.py:206).  Buckets are clamped to the
+ * int16 range (fuel below -327,680 only). */
+int shipenv_discretize(shipenv_ctx *ctx, const shipenv_ship *ships, int16_t *keys, int64_t n, void *stream);
+
 /* MCTSAgent._rollout (agents/mcts.py:211-238) from copies of R root ships, S rollouts each,
  * at most L accepted steps.  Rollout (r, s) draws one continuous word stream from the cell
  * (seed ^ "ROLL"<<32, root_id_base + r, s).  returns[r*S+s] is the fp64 sum of step rewards;

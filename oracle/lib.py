@@ -120,6 +120,12 @@ class Oracle:
         return ret, fin, steps, status
 
 
+def discretize(ships):
+    keys = np.zeros((len(ships), 6), np.int16)
+    lib().orc_discretize(_p(ships), _p(keys), C.c_int64(len(ships)))
+    return keys
+
+
 def ships_from(pos, cargo, fuel_bits):
     """Build a ship array from golden-fixture columns (pos u8[N,4], cargo i32, fuel u64 bits)."""
     s = np.zeros(len(cargo), SHIP_DTYPE)

@@ -68,6 +68,7 @@ _SIGNATURES = {
                                         C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]),
     "shipenv_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "shipenv_valid_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "shipenv_discretize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "shipenv_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "shipenv_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
@@ -197,6 +198,9 @@ class Context:
 
     def valid_actions(self, ships, mask, n, stream):
         check(lib().shipenv_valid_actions(self._h, ships, mask, n, stream))
+
+    def discretize(self, ships, keys, n, stream):
+        check(lib().shipenv_discretize(self._h, ships, keys, n, stream))
 
     def rollout(self, roots, R, S, L, returns, final, steps, status, seed, root_id_base, stream):
         check(lib().shipenv_rollout(self._h, roots, R, S, L, returns, final, steps, status, seed, root_id_base,

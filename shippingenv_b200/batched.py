@@ -94,7 +94,7 @@ class BatchedEnvironment:
         self.done_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
         self.reset_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
         self.error_bits = torch.zeros(nw, dtype=torch.int32, device=dev)
-        self._reward64 = self._status = self._taken = self._obs = self._valid = None
+        self._reward64 = self._status = self._taken = self._obs = self._valid = self._keys = None
         self.ep_return = self.stats = None
         if track_stats:
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -208,6 +208,13 @@ class BatchedEnvironment:
         bits = self.valid_action_bits()
         shifts = torch.arange(32, device=self.device, dtype=torch.int32)
         return ((bits[:, :, None] >> shifts) & 1).reshape(self.n, -1)[:, :self.num_actions].bool()
+
+    def discretize(self, out=None):
+        """``discretize_state`` keys of the tabular agents: int16 [N, 6] = x, y, "cargo" bucket, fuel bucket,
+        origin | -1, dest | -1 (utils/preprocessing.py:65-90)."""
+        k = out if out is not None else self._buf("_keys", (self.n, 6), torch.int16)
+        self.ctx.discretize(self.ships.data_ptr(), k.data_ptr(), self.n, self._stream())
+        return k
 
     def sample_action(self, word0=0):
         """``Environment.sample_action`` per env -> (actions int16 [N], words_used uint8 [N], status uint8 [N])."""

@@ -815,6 +815,28 @@ __global__ void __launch_bounds__(kThreads) valid_actions_kernel(const ValidArgs
 }
 
 // ------------------------------------------------------------------------------------------
+// discretize_state (utils/preprocessing.py:65-90): six int16 per env, no world needed
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bucket(double v, double width) {   // min(int(v / width), 4), int() truncates
+  const double q = __ddiv_rn(v, width);
+  const int b = q >= 2147483520.0 ? 2147483647 : q <= -2147483520.0 ? -2147483647 : __double2int_rz(q);
+  return max(min(b, 4), -32768);
+}
+
+__global__ void __launch_bounds__(kThreads) discretize_kernel(const uint4* __restrict__ ships, int16_t* __restrict__ keys,
+                                                              int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kThreads) {
+    const ShipR s = unpack(ships[i]);
+    int16_t* k = keys + i * 6;
+    k[0] = int16_t(s.x); k[1] = int16_t(s.y);
+    k[2] = int16_t(bucket(s.fuel, 10.0));      // the state dict's "cargo" is fuel (shipping/environment.py:206)
+    k[3] = int16_t(bucket(s.fuel, 20.0));
+    k[4] = s.origin == kNone ? int16_t(-1) : int16_t(s.origin);
+    k[5] = s.dest == kNone ? int16_t(-1) : int16_t(s.dest);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // MCTS rollouts: the whole simulations x max_rollout_steps loop in one kernel
 // ------------------------------------------------------------------------------------------
 struct RolloutArgs {

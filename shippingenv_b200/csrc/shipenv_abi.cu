@@ -413,6 +413,20 @@ int shipenv_valid_actions(shipenv_ctx* c, const shipenv_ship* ships, uint32_t* m
   return 0;
 }
 
+int shipenv_discretize(shipenv_ctx* c, const shipenv_ship* ships, int16_t* keys, int64_t n, void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (n < 0 || (n > 0 && (!ships || !keys))) return fail(SHIPENV_E_ARG, "discretize: null buffer or negative n");
+  if (n == 0) return 0;
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t tiles = (n + kThreads - 1) / kThreads;
+  const int grid = int(tiles < int64_t(c->sm_count) * 8 ? tiles : int64_t(c->sm_count) * 8);
+  discretize_kernel<<<grid, kThreads, 0, stream>>>(reinterpret_cast<const uint4*>(ships), keys, n);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
 int shipenv_rollout(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S, int L, double* returns,
                     shipenv_ship* final, int32_t* steps, uint8_t* status, uint64_t seed, uint64_t root_id_base,
                     void* stream_) {

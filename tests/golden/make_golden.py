@@ -126,11 +126,44 @@ def valid_action_golden(ns):
           float(np.concatenate(valid).sum(1).mean()))
 
 
+def discretize_golden(ns):
+    """g10: the reference's discretize_state (utils/preprocessing.py:65-90) on trajectory and edge states."""
+    PORTS = ns.consts.DEFAULT_PORTS
+    b = RefBatch(ns, 64, SEED, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.reset()
+    pos, cargo, fuel, keys = [], [], [], []
+
+    def snapshot():
+        p, c, f = b.states()
+        pos.append(p); cargo.append(c); fuel.append(f)
+        rows = []
+        for e in b.envs:
+            (x, y), cb, fb, prev, dest = ns.prep.discretize_state(e._build_state())
+            rows.append([x, y, max(cb, -32768), max(fb, -32768), prev, dest])
+        keys.append(np.array(rows, np.int16))
+
+    snapshot()
+    for t in range(230):
+        b.step(np.full(64, POLICY), 0, False)
+        if t % 23 == 0:
+            snapshot()
+    edge = [0.0, -0.0, 9.999999999999998, 10.0, 19.999, 20.0, 39.99999, 40.0, 49.9, 50.0, 79.99, 80.0, 99.9, 100.0,
+            1e6, -0.5, -9.99, -10.0, -19.9, -20.0, -20.00001, -399.9, -1e4, 1e300, 199.99, 200, 5e-324, 30, 60.0]
+    for i, f in enumerate(edge):
+        b.set_state(i, 10 + i, 20, NONE_PORT if i % 3 == 0 else i % 5, NONE_PORT if i % 4 == 0 else (i + 1) % 5, i, f)
+    snapshot()
+    save("g10_discretize", pos=np.concatenate(pos), cargo=np.concatenate(cargo), fuel=np.concatenate(fuel),
+         keys=np.concatenate(keys))
+
+
 def main():
     ns = import_reference()
     PORTS = ns.consts.DEFAULT_PORTS
     if "valid" in sys.argv[1:]:
         valid_action_golden(ns)
+        return
+    if "discretize" in sys.argv[1:]:
+        discretize_golden(ns)
         return
 
     # --- self-check: the reference imported here is the program SURVEY App. C hashed ----
@@ -321,6 +354,7 @@ def main():
     save("g8_rollouts", **out, **port_meta(b))
 
     valid_action_golden(ns)
+    discretize_golden(ns)
 
 
 if __name__ == "__main__":

@@ -299,3 +299,22 @@ def test_cuda_valid_action_mask(torch_cuda, default_map):
         ships, _ = env.state_numpy()
         want = o.valid_actions(ships.view(orc.SHIP_DTYPE).reshape(-1))
         assert (env.valid_action_mask().cpu().numpy() == want.astype(bool)).all(), t
+
+
+def test_cuda_discretize(torch_cuda):
+    """discretize_state keys on device == the reference's (fixture g10) == the oracle on random records."""
+    from shippingenv_b200 import BatchedEnvironment
+    z = golden("g10_discretize")
+    n = len(z["cargo"])
+    env = BatchedEnvironment(n, passable=golden("default_map")["passable"], device="cuda:0")
+    env.load_state(orc.ships_from(z["pos"], z["cargo"], z["fuel"]))
+    assert (env.discretize().cpu().numpy() == z["keys"]).all()
+    rng = np.random.default_rng(1)
+    n = 100_000
+    s = np.zeros(n, orc.SHIP_DTYPE)
+    s["x"], s["y"] = rng.integers(0, 100, n), rng.integers(0, 100, n)
+    s["origin"], s["dest"] = rng.choice([0, 1, 2, 3, 4, 255], n), rng.choice([0, 1, 2, 3, 4, 255], n)
+    s["fuel"] = np.where(rng.random(n) < 0.5, rng.random(n) * 260 - 60, rng.integers(-30, 30, n) * 10.0)
+    env = BatchedEnvironment(n, passable=golden("default_map")["passable"], device="cuda:0")
+    env.load_state(s)
+    assert (env.discretize().cpu().numpy() == orc.discretize(s)).all()
