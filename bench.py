@@ -333,6 +333,11 @@ def run_ours(args):
         extras["mcts_rollouts"] = {"roots": R, "simulations": S, "max_rollout_steps": L, "ms_per_launch": ms,
                                    "rollout_steps_per_s": rsteps / (ms * 1e-3), "roots_per_s": R / (ms * 1e-3),
                                    "what": "MCTSAgent._rollout x 50 per root in one kernel (reference: 5.6 roots/s/core)"}
+        ms = timed(lambda: g0.mcts(S, L, roots=roots), 2)
+        extras["mcts_choose_action"] = {"roots": R, "simulations": S, "max_rollout_steps": L, "ms_per_launch": ms,
+                                        "decisions_per_s": R / (ms * 1e-3),
+                                        "what": "MCTSAgent.choose_action (UCB1 tree + expansion + rollouts + backprop) per "
+                                                "root in one kernel; reference: 0.18 s per decision per core"}
 
     # ---- max over ranks ----
     times = torch.tensor([total_ms, flushed_ms, e2e_ms], dtype=torch.float64, device=dev)

@@ -185,6 +185,25 @@ int shipenv_rollout(shipenv_ctx *ctx, const shipenv_ship *roots, int64_t R, int 
                     double *returns, shipenv_ship *final, int32_t *steps, uint8_t *status,
                     uint64_t seed, uint64_t root_id_base, void *stream);
 
+/* MCTSAgent.choose_action (agents/mcts.py:240-292) for R roots, one tree per root, entirely on the device:
+ * S simulations of UCB1 selection (:109-128, :260-268), expansion by random.choice of an untried action
+ * (:271-279), _rollout of at most L accepted steps (:211-238) and backpropagation (:149-159), then the
+ * final pick with c = 0 (:288-290).  Simulation s of root r draws from the rollout cell (root_id_base + r, s):
+ * tree-phase draws first, the rollout continues the same stream.  Nodes whose recorded state is not the
+ * four-move case (destination unset, or fuel == 0 at a port: get_possible_actions :63-77) end the root with
+ * status SHIPENV_ST_MCTS_UNSUPPORTED; a root without children (:291-292) gets SHIPENV_ST_MCTS_NO_CHILDREN and
+ * action -1.  log_table is a HOST array with log_table[n] = log(n) for n = 1..S+1 (index 0 unused), or NULL to
+ * let the library fill it with the C library's log(); passing numpy.log values makes UCB1 bit-identical to
+ * the reference.  S <= SHIPENV_MCTS_MAX_SIMS.  Outputs (device): action[R] flat move index, root_visits[R],
+ * child_action / child_visits / child_total [R, 4] in expansion order (-1 / 0 / 0 when absent), status[R]. */
+#define SHIPENV_MCTS_MAX_SIMS 126
+#define SHIPENV_ST_MCTS_UNSUPPORTED 10
+#define SHIPENV_ST_MCTS_NO_CHILDREN 11
+int shipenv_mcts(shipenv_ctx *ctx, const shipenv_ship *roots, int64_t R, int S, int L, double c_param,
+                 const double *log_table, int16_t *action, int32_t *root_visits, int16_t *child_action,
+                 int32_t *child_visits, double *child_total, uint8_t *status, uint64_t seed,
+                 uint64_t root_id_base, void *stream);
+
 /* ---- host-side helpers (no GPU) ------------------------------------------------------ */
 /* Philox4x32-10 block (the word-stream definition). */
 void shipenv_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

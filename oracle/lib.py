@@ -120,6 +120,20 @@ class Oracle:
         return ret, fin, steps, status
 
 
+def mcts(oracle, roots, S, L, seed, root_base=0, c_param=1.4):
+    """MCTSAgent.choose_action per root -> dict(action, root_visits, child_action/visits/total [R,4], status)."""
+    R = len(roots)
+    out = dict(action=np.zeros(R, np.int16), root_visits=np.zeros(R, np.int32),
+               child_action=np.zeros((R, 4), np.int16), child_visits=np.zeros((R, 4), np.int32),
+               child_total=np.zeros((R, 4), np.float64), status=np.zeros(R, np.uint8))
+    log_table = np.concatenate([[0.0], np.log(np.arange(1, max(S, 1) + 2))])
+    lib().orc_mcts(C.byref(oracle.w), _p(roots), C.c_int64(R), C.c_int(S), C.c_int(L), C.c_double(c_param),
+                   _p(log_table), _p(out["action"]), _p(out["root_visits"]), _p(out["child_action"]),
+                   _p(out["child_visits"]), _p(out["child_total"]), _p(out["status"]), C.c_uint64(seed),
+                   C.c_uint64(root_base))
+    return out
+
+
 def discretize(ships):
     keys = np.zeros((len(ships), 6), np.int16)
     lib().orc_discretize(_p(ships), _p(keys), C.c_int64(len(ships)))

@@ -234,3 +234,45 @@ def ref_rollout(ns, shim, env, root_id, sim, max_steps):
     shim.seek_rollout(root_id, sim)
     total = agent._rollout(copy, None)
     return total, copy
+
+
+def ref_mcts_decide(ns, shim, env, root_id, sims, max_rollout_steps, c_param=1.4):
+    """Unmodified ``MCTSAgent.choose_action`` (agents/mcts.py:240-292) on ``env``.
+
+    The agent's own ``random`` (``random.choice(untried)``, agents/mcts.py:274) and the environment's draws
+    both come from the shim; simulation ``s`` of root ``root_id`` reads the stream cell (root_id, s) -- the
+    same cell the rollout kernel uses -- which is arranged by wrapping ``_create_env_copy`` (called once at
+    the top of every simulation, agents/mcts.py:257) with a seek.  No reference file is edited.
+    Returns (action, root) with ``root`` the reference's MCTSNode tree.
+    """
+    ns.mcts.random = shim
+    agent = ns.mcts.MCTSAgent.__new__(ns.mcts.MCTSAgent)
+    agent.env = env
+    agent.num_simulations = sims
+    agent.exploration_param = c_param
+    agent.max_rollout_steps = max_rollout_steps
+    agent.map_file = ns.map_path
+    counter = [0]
+    original = ns.mcts.MCTSAgent._create_env_copy
+
+    def positioned_copy():
+        shim.seek_rollout(root_id, counter[0])
+        counter[0] += 1
+        return original(agent)
+
+    agent._create_env_copy = positioned_copy
+    captured = {}
+    node_cls = ns.mcts.MCTSNode
+    real_init = node_cls.__init__
+
+    def spy_init(self, state, action=None, parent=None):
+        real_init(self, state, action=action, parent=parent)
+        if parent is None and action is None:
+            captured["root"] = self
+
+    node_cls.__init__ = spy_init
+    try:
+        action = agent.choose_action(env._build_state())
+    finally:
+        node_cls.__init__ = real_init
+    return action, captured["root"]

@@ -22,6 +22,7 @@ F_AUTO_RESET = 1
 
 (ST_OK, ST_OFF_MAP, ST_NO_DEST, ST_SEL_RANGE, ST_SEL_ORIGIN, ST_NOT_AT_PORT, ST_BAD_AMOUNT,
  ST_UNKNOWN, ST_NO_PORTS, ST_SAMPLE_CRASH) = range(10)
+ST_MCTS_UNSUPPORTED, ST_MCTS_NO_CHILDREN, MCTS_MAX_SIMS = 10, 11, 126
 
 
 class ShipEnvError(RuntimeError):
@@ -71,6 +72,9 @@ _SIGNATURES = {
     "shipenv_discretize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "shipenv_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "shipenv_mcts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                               C.c_uint64, C.c_void_p]),
     "shipenv_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "shipenv_port_stock": (None, [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]),
     "shipenv_launch_count": (C.c_uint64, []),
@@ -201,6 +205,11 @@ class Context:
 
     def discretize(self, ships, keys, n, stream):
         check(lib().shipenv_discretize(self._h, ships, keys, n, stream))
+
+    def mcts(self, roots, R, S, L, c_param, log_table, action, root_visits, child_action, child_visits, child_total,
+             status, seed, root_id_base, stream):
+        check(lib().shipenv_mcts(self._h, roots, R, S, L, c_param, log_table, action, root_visits, child_action,
+                                 child_visits, child_total, status, seed, root_id_base, stream))
 
     def rollout(self, roots, R, S, L, returns, final, steps, status, seed, root_id_base, stream):
         check(lib().shipenv_rollout(self._h, roots, R, S, L, returns, final, steps, status, seed, root_id_base,

@@ -248,6 +248,28 @@ class BatchedEnvironment:
             raise ValueError("construct with track_stats=True")
         return summarize(reduce_stats(self.stats, group))
 
+    def mcts(self, simulations=50, max_rollout_steps=100, c_param=1.4, roots=None, root_id_base=None):
+        """``MCTSAgent.choose_action`` for every root (default: the current ships), trees on the device.
+
+        Returns dict: ``action`` int16 [R] (flat move index, -1 without children), ``root_visits`` int32 [R],
+        ``child_action`` / ``child_visits`` / ``child_total`` [R, 4] in expansion order, ``status`` uint8 [R]."""
+        roots = self.ships if roots is None else roots
+        R, dev = roots.shape[0], self.device
+        out = dict(action=torch.empty(R, dtype=torch.int16, device=dev),
+                   root_visits=torch.empty(R, dtype=torch.int32, device=dev),
+                   child_action=torch.empty((R, 4), dtype=torch.int16, device=dev),
+                   child_visits=torch.empty((R, 4), dtype=torch.int32, device=dev),
+                   child_total=torch.empty((R, 4), dtype=torch.float64, device=dev),
+                   status=torch.empty(R, dtype=torch.uint8, device=dev))
+        # numpy.log, so that UCB1 is bit-identical to the reference's np.log (agents/mcts.py:125)
+        log_table = np.concatenate([[0.0], np.log(np.arange(1, simulations + 2))])
+        base = self.env_id_base if root_id_base is None else root_id_base
+        self.ctx.mcts(roots.data_ptr(), R, simulations, max_rollout_steps, c_param, log_table.ctypes.data,
+                      out["action"].data_ptr(), out["root_visits"].data_ptr(), out["child_action"].data_ptr(),
+                      out["child_visits"].data_ptr(), out["child_total"].data_ptr(), out["status"].data_ptr(),
+                      self.seed, base, self._stream())
+        return out
+
     # ---- host <-> device state ----------------------------------------------------------
     def load_state(self, ships_np, clock_np=None):
         """Overwrite the ship records (numpy structured/uint8 [N,16]) and optionally the clock."""

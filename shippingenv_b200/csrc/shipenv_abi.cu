@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -63,6 +64,7 @@ struct shipenv_ctx {
   shipenv_consts consts = kDefaultConsts;
   // device blob
   void* d_world = nullptr;
+  double* d_log_table = nullptr;        // shipenv_mcts: log(n), n = 0..SHIPENV_MCTS_MAX_SIMS+1
   uint32_t* d_tile_counter = nullptr;   // ticket counter of step_fast_kernel's tile scheduler
   uint32_t tile_base = 0;
   std::vector<unsigned char> h_world;
@@ -71,7 +73,7 @@ struct shipenv_ctx {
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_step_fast, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid;
+  Occ occ_step_fast, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid, occ_mcts;
 };
 
 namespace {
@@ -209,6 +211,8 @@ int shipenv_ctx_create(int device, shipenv_ctx** out) {
   CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   cudaError_t e = cudaMalloc(&c->d_world, kMaxWorldBytes);
   if (e != cudaSuccess) { delete c; return fail(SHIPENV_E_CUDA, "cudaMalloc(world): %s", cudaGetErrorString(e)); }
+  e = cudaMalloc(&c->d_log_table, sizeof(double) * (SHIPENV_MCTS_MAX_SIMS + 2));
+  if (e != cudaSuccess) { cudaFree(c->d_world); delete c; return fail(SHIPENV_E_CUDA, "log table: %s", cudaGetErrorString(e)); }
   e = cudaMalloc(&c->d_tile_counter, 256);
   if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 256);
   if (e != cudaSuccess) { cudaFree(c->d_world); delete c; return fail(SHIPENV_E_CUDA, "tile counter: %s", cudaGetErrorString(e)); }
@@ -222,6 +226,7 @@ int shipenv_ctx_destroy(shipenv_ctx* c) {
     DeviceGuard guard(c->device);
     if (c->d_world) cudaFree(c->d_world);
     if (c->d_tile_counter) cudaFree(c->d_tile_counter);
+    if (c->d_log_table) cudaFree(c->d_log_table);
   }
   delete c;
   return 0;
@@ -445,6 +450,35 @@ int shipenv_rollout(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S,
   int grid = 0;
   if (int rc = grid_for(c, rollout_kernel, c->occ_rollout, kRolloutThreads, smem, tiles, &grid)) return rc;
   rollout_kernel<<<grid, kRolloutThreads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int shipenv_mcts(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S, int L, double c_param,
+                 const double* log_table, int16_t* action, int32_t* root_visits, int16_t* child_action,
+                 int32_t* child_visits, double* child_total, uint8_t* status, uint64_t seed, uint64_t root_id_base,
+                 void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (R < 0 || S < 0 || L < 0) return fail(SHIPENV_E_ARG, "mcts: negative size");
+  if (S > SHIPENV_MCTS_MAX_SIMS) return fail(SHIPENV_E_ARG, "mcts: at most %d simulations", SHIPENV_MCTS_MAX_SIMS);
+  if (R > 0 && (!roots || !action || !root_visits || !child_action || !child_visits || !child_total || !status))
+    return fail(SHIPENV_E_ARG, "mcts: null buffer");
+  if (R == 0) return 0;
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  double table[SHIPENV_MCTS_MAX_SIMS + 2];
+  table[0] = 0.0;
+  for (int n = 1; n < S + 2; ++n) table[n] = log_table ? log_table[n] : std::log(double(n));
+  CUDA_TRY(cudaMemcpyAsync(c->d_log_table, table, sizeof(double) * (S + 2), cudaMemcpyHostToDevice, stream));
+  MctsArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, c_param, c->d_log_table,
+             action, root_visits, child_action, child_visits, child_total, status, seed, root_id_base, {}};
+  fill_round_keys(a.round_key, seed, kRolloutTweak);
+  const size_t smem = c->world_bytes;
+  int grid = 0;
+  if (int rc = grid_for(c, mcts_kernel, c->occ_mcts, kMctsThreads, smem, (R + kMctsThreads - 1) / kMctsThreads, &grid)) return rc;
+  mcts_kernel<<<grid, kMctsThreads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   ++g_launches;
   return 0;

@@ -126,6 +126,41 @@ def valid_action_golden(ns):
           float(np.concatenate(valid).sum(1).mean()))
 
 
+def mcts_golden(ns):
+    """g11: the reference's MCTSAgent.choose_action (agents/mcts.py:240-292), 50 simulations x 100-step rollouts
+    (and a 12 x 20 variant), on roots reached by the random policy plus roots at the map border / low on fuel."""
+    from oracle.ref_harness import ref_mcts_decide
+    PORTS = ns.consts.DEFAULT_PORTS
+    R = 40
+    b = RefBatch(ns, R, SEED, PORTS, STOCK_FUEL, STOCK_CARGO)
+    b.reset()
+    for t in range(10):
+        b.step(np.full(R, POLICY), 0, False)
+    b.set_state(0, 0, 50, 1, 2, 4, 150.0)          # on the western border: one move is off-map for ever
+    b.set_state(1, 99, 0, 1, 2, 0, 88.5)           # in a corner
+    b.set_state(2, 61, 72, 4, 1, 9, 2.5)           # about to run out of fuel
+    b.set_state(3, 60, 23, 4, 1, 12, 120.0)        # next to its destination
+    rp, rc, rf = b.states()
+    out = dict(root_pos=rp, root_cargo=rc, root_fuel=rf)
+    move_idx = {(0, -1): 0, (-1, 0): 1, (0, 1): 2, (1, 0): 3}
+    for S, L in ((50, 100), (12, 20)):
+        act = np.full(R, -1, np.int16); rv = np.zeros(R, np.int32)
+        ca = np.full((R, 4), -1, np.int16); cv = np.zeros((R, 4), np.int32); ct = np.zeros((R, 4), np.uint64)
+        for r in range(R):
+            a, root = ref_mcts_decide(ns, b.shim, b.envs[r], 7000 + r, S, L)
+            act[r] = move_idx[tuple(a[1])]
+            rv[r] = root.visits
+            for k, ch in enumerate(root.children):
+                ca[r, k] = move_idx[tuple(ch.action[1])]; cv[r, k] = ch.visits; ct[r, k] = f64_bits(ch.total_reward)
+        tag = f"S{S}_L{L}"
+        out[f"action_{tag}"], out[f"root_visits_{tag}"] = act, rv
+        out[f"child_action_{tag}"], out[f"child_visits_{tag}"], out[f"child_total_{tag}"] = ca, cv, ct
+        print(f"  mcts {tag}: action histogram", np.bincount(act, minlength=4), " mean root visits", rv.mean())
+    out["root_id_base"] = np.uint64(7000)
+    out["seed"] = np.uint64(SEED)
+    save("g11_mcts", **out, **port_meta(b))
+
+
 def discretize_golden(ns):
     """g10: the reference's discretize_state (utils/preprocessing.py:65-90) on trajectory and edge states."""
     PORTS = ns.consts.DEFAULT_PORTS
@@ -164,6 +199,9 @@ def main():
         return
     if "discretize" in sys.argv[1:]:
         discretize_golden(ns)
+        return
+    if "mcts" in sys.argv[1:]:
+        mcts_golden(ns)
         return
 
     # --- self-check: the reference imported here is the program SURVEY App. C hashed ----
@@ -355,6 +393,7 @@ def main():
 
     valid_action_golden(ns)
     discretize_golden(ns)
+    mcts_golden(ns)
 
 
 if __name__ == "__main__":

@@ -318,3 +318,44 @@ def test_cuda_discretize(torch_cuda):
     env = BatchedEnvironment(n, passable=golden("default_map")["passable"], device="cuda:0")
     env.load_state(s)
     assert (env.discretize().cpu().numpy() == orc.discretize(s)).all()
+
+
+@pytest.mark.parametrize("S,L", [(50, 100), (12, 20)])
+def test_cuda_mcts_matches_reference_choose_action(torch_cuda, S, L):
+    """The on-device MCTS (tree + rollouts in one kernel) against the unmodified reference agent (fixture g11)."""
+    from shippingenv_b200 import BatchedEnvironment
+    z = golden("g11_mcts")
+    roots = orc.ships_from(z["root_pos"], z["root_cargo"], z["root_fuel"])
+    env = BatchedEnvironment(len(roots), passable=z["passable"], seed=int(z["seed"]), device="cuda:0")
+    env.load_state(roots)
+    out = {k: v.cpu().numpy() for k, v in env.mcts(S, L, root_id_base=int(z["root_id_base"])).items()}
+    tag = f"S{S}_L{L}"
+    assert (out["status"] == 0).all()
+    assert (out["action"] == z[f"action_{tag}"]).all()
+    assert (out["root_visits"] == z[f"root_visits_{tag}"]).all()
+    assert (out["child_action"] == z[f"child_action_{tag}"]).all()
+    assert (out["child_visits"] == z[f"child_visits_{tag}"]).all()
+    assert (out["child_total"].view(np.uint64) == z[f"child_total_{tag}"]).all()
+
+
+def test_cuda_mcts_vs_oracle_large(torch_cuda, default_map):
+    """4,096 roots x 50 simulations x 100-step rollouts (BASELINE config 4 shape) against the oracle, plus roots
+    that the tree cannot handle (no destination) and a root without any legal expansion."""
+    from shippingenv_b200 import BatchedEnvironment
+    R, seed = 4096, 4242
+    env = BatchedEnvironment(R, passable=default_map["passable"], seed=seed, device="cuda:0", auto_reset=False)
+    env.reset()
+    for _ in range(12):
+        env.step_policy()
+    roots, _ = env.state_numpy()
+    roots = roots.view(orc.SHIP_DTYPE).reshape(-1).copy()
+    roots["dest"][:3] = 255                         # unsupported node state -> status 10
+    env.load_state(roots)
+    o = orc.Oracle(default_map["passable"], env.ports, env.port_fuel, env.port_cargo)
+    want = orc.mcts(o, roots, 50, 100, seed)
+    got = {k: v.cpu().numpy() for k, v in env.mcts(50, 100).items()}
+    assert (got["status"] == want["status"]).all() and (got["status"][:3] == 10).all() and (got["status"][3:] == 0).all()
+    for k in ("action", "root_visits", "child_action", "child_visits"):
+        assert (got[k] == want[k]).all(), k
+    assert (got["child_total"].view(np.uint64) == want["child_total"].view(np.uint64)).all()
+    assert len(np.unique(got["action"][3:])) == 4
