@@ -217,6 +217,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as entry
+    if local == 0:
+        entry.build()                     # no-op when the shipped library matches the sources
+    if world_size > 1:
+        dist.barrier()
 
     n = args.envs
     G = args.groups
@@ -405,10 +410,10 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    import __graft_entry__ as entry
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        entry.build()
     if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            from oracle import lib as oracle_lib
+            oracle_lib.build()
         run_reference(args)
     else:
         run_ours(args)

@@ -39,9 +39,14 @@ DEFAULT_CONSTS = dict(
 
 
 def build(force=False):
+    import hashlib
     src = os.path.join(HERE, "shipenv_oracle.c")
-    if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src):
+    digest = hashlib.sha256(open(src, "rb").read() + open(os.path.join(HERE, "Makefile"), "rb").read()).hexdigest()
+    stamp = SO + ".srchash"
+    if force or not os.path.exists(SO) or not os.path.exists(stamp) or open(stamp).read().strip() != digest:
         subprocess.run(["make", "-C", HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as f:
+            f.write(digest)
     return SO
 
 
