@@ -75,6 +75,8 @@ enum {
 
 /* step flags */
 #define SHIPENV_F_AUTO_RESET 1u   /* reset an env in the step that ends its episode (done or truncated) */
+#define SHIPENV_F_ALL_POLICY 2u   /* every action of this call is SHIPENV_ACT_POLICY; `actions` is not read and may
+                                     be NULL when only reward_f32 and the three masks are requested */
 
 /* One ship, 16 bytes, moved as a single 128-bit load/store.  Mirrors the attributes
  * Environment keeps per ship (shipping/environment.py:37-41). */

@@ -19,6 +19,7 @@ ACT_EXT_FUEL = 0x6000
 N_CARGO_ACTIONS = 50
 N_FUEL_ACTIONS = 200
 F_AUTO_RESET = 1
+F_ALL_POLICY = 2
 
 (ST_OK, ST_OFF_MAP, ST_NO_DEST, ST_SEL_RANGE, ST_SEL_ORIGIN, ST_NOT_AT_PORT, ST_BAD_AMOUNT,
  ST_UNKNOWN, ST_NO_PORTS, ST_SAMPLE_CRASH) = range(10)

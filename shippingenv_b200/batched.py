@@ -150,8 +150,9 @@ class BatchedEnvironment:
             cached = self._step_cache[key] = self._build_step_io(want_obs, want_status, want_taken, want_reward64,
                                                                  obs_out)
         io_ref, res = cached
+        flags = (nat.F_AUTO_RESET if self.auto_reset else 0) | (nat.F_ALL_POLICY if actions is self._policy else 0)
         rc = self._lib_step(self._ctx_handle, self._ships_ptr, self._clock_ptr, actions.data_ptr(), io_ref, self.seed,
-                            self.env_id_base, self.n, self.max_steps, nat.F_AUTO_RESET if self.auto_reset else 0,
+                            self.env_id_base, self.n, self.max_steps, flags,
                             word0, torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             nat.check(rc)

@@ -228,7 +228,7 @@ __device__ __forceinline__ uint32_t step_general_inline(const StepArgs& a, const
   const WorldView w(world_smem);
   const uint4 rec = a.ships[i];
   const uint32_t c = a.clock[i];
-  const int act = a.actions[i];
+  const int act = (a.flags & SHIPENV_F_ALL_POLICY) ? SHIPENV_ACT_POLICY : int(a.actions[i]);
   ShipR s = unpack(rec);
   Rng g;
   g.seek(a.round_key, c, a.env_id_base + uint64_t(uint32_t(i)), a.word0);
@@ -492,6 +492,9 @@ constexpr int kDeferCap = 64;   // per-warp deferred-env list; a tile adds at mo
 #ifndef SHIPENV_FAST_MIN_BLOCKS
 #define SHIPENV_FAST_MIN_BLOCKS 3
 #endif
+// kPolicy: every action of the launch is SHIPENV_ACT_POLICY (SHIPENV_F_ALL_POLICY); the straight-line case is then
+// `sample_action` choosing a MOVE (word 0) followed by that move (words 1, 2); `actions` is never read.
+template <bool kPolicy>
 __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
@@ -534,10 +537,10 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         }
         const int base = int(ticket) * kThreads;
         stage_tile[st] = int(ticket);
-        mbar_expect_tx(&full_bar[st], uint32_t(sizeof(TileStage)));
+        mbar_expect_tx(&full_bar[st], kThreads * (kPolicy ? 20u : 22u));
         tma_load_bulk(stage[st].ships, a.ships + base, kThreads * 16u, &full_bar[st]);
         tma_load_bulk(stage[st].clock, a.clock + base, kThreads * 4u, &full_bar[st]);
-        tma_load_bulk(stage[st].act, a.actions + base, kThreads * 2u, &full_bar[st]);
+        if (!kPolicy) tma_load_bulk(stage[st].act, a.actions + base, kThreads * 2u, &full_bar[st]);
         ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base;   // in flight while the slot is awaited
       }
     }
@@ -581,27 +584,35 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const uint32_t so = st * uint32_t(sizeof(TileStage));
       const uint4 rec = lds_u4(my_ship + so);
       const uint32_t c = lds_u32(my_clock + so);
-      const int act = lds_s16(my_act + so);
+      const int act = kPolicy ? SHIPENV_ACT_POLICY : lds_s16(my_act + so);
       __syncwarp();
       if (lane == 0) mbar_arrive_s(empty_b + st * 8u);
       st = (st + 1u) & uint32_t(kStages - 1);
       parity ^= uint32_t(st == 0u);
 
       const uint32_t x = rec.x & 255u, y = (rec.x >> 8) & 255u, dest = rec.x >> 24;
-      // N,E,S,W = (0,-1),(-1,0),(0,1),(1,0): odd actions move along x, even ones along y
-      const int m = act & 3;
-      const int dx = (m & 1) * (m - 2), dy = ((m & 1) ^ 1) * (m - 1);
-      const uint32_t nx = x + uint32_t(dx), ny = y + uint32_t(dy);
-      const bool is_move = unsigned(act) < 4u && dest != uint32_t(kNone);
-      const bool in_map = nx < W && ny < H;          // unsigned: -1 wraps to a huge value  (:284)
-      // Philox block 0 of the (env, clock) cell: words 0,1 = fuel-cost and cargo-loss draws, 2,3 = reset draws
+      // Philox block 0 of the (env, clock) cell.  Explicit action: words 0,1 = fuel-cost and cargo-loss draws,
+      // 2,3 = reset draws.  Policy: word 0 = choice([N,E,S,W]) (:165-167), 1,2 = the move's draws.
       uint32_t wd[4];
       {
         const uint32_t lo = id_lo + uint32_t(i);
         philox_rk(0u, c, lo, id_hi + uint32_t(lo < id_lo), a.round_key, wd);
       }
-      const double cost = __dadd_rn(1.0, __dadd_rn(-0.1, __dmul_rn(0.1 - (-0.1), unit_double(wd[0]))));   // :103-104
+      const uint32_t w_cost = kPolicy ? wd[1] : wd[0], w_loss = kPolicy ? wd[2] : wd[1];
       const double fuel = __hiloint2double(int(rec.w), int(rec.z));
+      // N,E,S,W = (0,-1),(-1,0),(0,1),(1,0): odd actions move along x, even ones along y
+      const int m = kPolicy ? int(__umulhi(wd[0], 4u)) : (act & 3);
+      const int dx = (m & 1) * (m - 2), dy = ((m & 1) ^ 1) * (m - 1);
+      const uint32_t nx = x + uint32_t(dx), ny = y + uint32_t(dy);
+      bool is_move;
+      if (kPolicy) {   // sample_action (:245-263) picks a MOVE unless the ship sits on a port with no cargo / no fuel
+        const bool on_port = (lds_u32(bits_b + (uint32_t(w.h->n_bit_words) + x * wpr + (y >> 5)) * 4u) >> (y & 31u)) & 1u;
+        is_move = dest != uint32_t(kNone) && !(on_port && (rec.y == 0u || fuel == 0.0));
+      } else {
+        is_move = unsigned(act) < 4u && dest != uint32_t(kNone);
+      }
+      const bool in_map = nx < W && ny < H;          // unsigned: -1 wraps to a huge value  (:284)
+      const double cost = __dadd_rn(1.0, __dadd_rn(-0.1, __dmul_rn(0.1 - (-0.1), unit_double(w_cost))));   // :103-104
       const bool no_fuel = fuel < cost;                                                   // :288
       const uint32_t cell = in_map ? nx * wpr + (ny >> 5) : 0u;
       const bool water = (lds_u32(bits_b + cell * 4u) >> (ny & 31u)) & 1u;                // :293
@@ -611,14 +622,16 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const bool closer = (int(x) - int(tx)) * dx + (int(y) - int(ty)) * dy < 0;
       const uint32_t px = water ? nx : x, py = water ? ny : y;
       // loss_thr[cap] = 0xFFFFFFFF: cargo >= capacity always draws; negative cargo goes the general way
-      const bool trigger = wd[1] <= lds_u32(wb + uint32_t(offsetof(WorldHdr, loss_thr)) + min(uint32_t(rec.y), cap) * 4u);  // :318-320
+      const bool trigger = w_loss <= lds_u32(wb + uint32_t(offsetof(WorldHdr, loss_thr)) + min(uint32_t(rec.y), cap) * 4u);  // :318-320
       const bool arrive = px == tx && py == ty;                                           // :325
       const uint32_t c1 = c + 1u;
       const bool do_reset = auto_reset && (no_fuel || (c1 & 0xFFFFu) >= trunc_at);
       const uint32_t ro = __umulhi(wd[2], P), rd = __umulhi(wd[3], P);                    // :232-233
-      const bool general = !is_move || (in_map && (trigger || arrive || (do_reset && ro == rd)));
+      // policy: an off-map choice is re-drawn and a reset needs words 3 and 4 -- both go the general way
+      const bool general = kPolicy ? (!is_move || !in_map || trigger || arrive || do_reset)
+                                   : (!is_move || (in_map && (trigger || arrive || (do_reset && ro == rd))));
       const bool ok = is_move && in_map && !general;
-      const bool off_map = is_move && !in_map;
+      const bool off_map = !kPolicy && is_move && !in_map;
       {
         const double fuel1 = water ? __dsub_rn(fuel, cost) : fuel;                        // :298
         uint4 out;

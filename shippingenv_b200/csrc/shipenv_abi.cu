@@ -73,7 +73,7 @@ struct shipenv_ctx {
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_step_fast, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid, occ_mcts;
+  Occ occ_step_fast, occ_step_fast_policy, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid, occ_mcts;
 };
 
 namespace {
@@ -298,7 +298,8 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
                  const shipenv_step_io* io, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
                  uint32_t flags, uint32_t word0, void* stream_) {
   if (int rc = check_ctx(c)) return rc;
-  if (n < 0 || (n > 0 && (!ships || !clock || !actions))) return fail(SHIPENV_E_ARG, "step: null buffer or negative n");
+  const bool all_policy = flags & SHIPENV_F_ALL_POLICY;
+  if (n < 0 || (n > 0 && (!ships || !clock || (!actions && !all_policy)))) return fail(SHIPENV_E_ARG, "step: null buffer or negative n");
   if (max_steps < 0 || max_steps > 65535) return fail(SHIPENV_E_ARG, "max_steps %d outside 0..65535", max_steps);
   if (n == 0) return 0;
   if (n >= (int64_t(1) << 31)) return fail(SHIPENV_E_ARG, "step: at most 2^31-1 envs per launch");
@@ -319,6 +320,7 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   const bool lean = !a.io.reward_f64 && !a.io.status && !a.io.taken && !a.io.ep_return;
   int grid = 0;
   if (a.io.obs) {
+    if (!actions) return fail(SHIPENV_E_ARG, "step: the observation variant needs the `actions` array");
     if (reinterpret_cast<uintptr_t>(a.io.obs) & 15u) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
     const size_t base = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + ((kPipeBytes + 127) & ~size_t(127));
     const size_t tile_bytes = size_t(kThreads) * a.obs_width * 4;
@@ -334,7 +336,8 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   } else if (lean && a.io.reward_f32 && a.io.done_bits && a.io.reset_bits && a.io.error_bits && word0 == 0 &&
              c->P >= 2 && !c->no_fast_kernel) {
     const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes + kDeferCap * 4 * (kThreads / 32);
-    if (int rc = grid_for(c, step_fast_kernel, c->occ_step_fast, kStepBlock, smem, tiles, &grid)) return rc;
+    if (int rc = all_policy ? grid_for(c, step_fast_kernel<true>, c->occ_step_fast_policy, kStepBlock, smem, tiles, &grid)
+                            : grid_for(c, step_fast_kernel<false>, c->occ_step_fast, kStepBlock, smem, tiles, &grid)) return rc;
     a.tile_counter = c->d_tile_counter;
     a.tile_base = c->tile_base;
     c->tile_base += uint32_t(n / kThreads) + uint32_t(grid);   // every tile once + one failed ticket per CTA
@@ -344,8 +347,10 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this grid's prologue
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // with the previous grid's tail
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, step_fast_kernel, a));
+    if (all_policy) CUDA_TRY(cudaLaunchKernelEx(&cfg, step_fast_kernel<true>, a));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, step_fast_kernel<false>, a));
   } else {
+    if (!actions) return fail(SHIPENV_E_ARG, "step: this output set needs the `actions` array even with SHIPENV_F_ALL_POLICY");
     const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes;
     if (lean) {
       if (int rc = grid_for(c, step_kernel<false, true>, c->occ_step, kStepBlock, smem, tiles, &grid)) return rc;

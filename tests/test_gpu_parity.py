@@ -359,3 +359,32 @@ def test_cuda_mcts_vs_oracle_large(torch_cuda, default_map):
         assert (got[k] == want[k]).all(), k
     assert (got["child_total"].view(np.uint64) == want["child_total"].view(np.uint64)).all()
     assert len(np.unique(got["action"][3:])) == 4
+
+
+@pytest.mark.parametrize("n,max_steps", [(1, 50), (300, 50), (70_001, 120)])
+def test_cuda_policy_fast_kernel(torch_cuda, default_map, n, max_steps):
+    """SHIPENV_F_ALL_POLICY through the throughput kernel (reward_f32 + masks only): sample_action + step in
+    the straight-line path, resets / cargo pick-up / loss / arrival / off-map re-draws through the deferred
+    general path -- every step bit-identical to the oracle's policy step."""
+    from shippingenv_b200 import BatchedEnvironment, unpack_bits
+    seed = 909
+    env = BatchedEnvironment(n, passable=default_map["passable"], seed=seed, device="cuda:0", max_steps=max_steps)
+    o = orc.Oracle(default_map["passable"], env.ports, env.port_fuel, env.port_cargo)
+    ships, clock = np.zeros(n, orc.SHIP_DTYPE), np.zeros(n, np.uint32)
+    env.reset(); o.reset(ships, clock, seed)
+    pol = np.full(n, -1, np.int16)
+    n_reset = n_arrive = 0
+    for t in range(260 if n < 1000 else 140):
+        r = env.step_policy()
+        ref = o.step(ships, clock, pol, seed, 0, max_steps, True)
+        g_ships, g_clock = env.state_numpy()
+        assert g_ships.tobytes() == ships.tobytes(), f"ships differ at step {t}"
+        assert (g_clock == clock).all()
+        assert (r.reward.cpu().numpy() == ref["reward"].astype(np.float32)).all()
+        assert (unpack_bits(r.done_bits, n).cpu().numpy() == ref["done"].astype(bool)).all()
+        assert (unpack_bits(r.reset_bits, n).cpu().numpy() == ref["reset"].astype(bool)).all()
+        assert (unpack_bits(r.error_bits, n).cpu().numpy() == (ref["status"] != 0)).all()
+        n_reset += int(ref["reset"].sum()); n_arrive += int((ref["reward"] > 5).sum())
+    assert n_reset > 0
+    if n > 1000:
+        assert n_arrive > 0

@@ -18,7 +18,8 @@ env.reset()
 gen = torch.Generator(device="cuda").manual_seed(1234)
 acts = [torch.randint(0, 4, (n,), generator=gen, device="cuda", dtype=torch.int16) for _ in range(8)]
 if args.mode == "policy":
-    acts = [torch.full((n,), -1, dtype=torch.int16, device="cuda")]
+    env.step_policy()
+    acts = [env._policy]          # the env's own policy tensor: step() then sets SHIPENV_F_ALL_POLICY
 kw = dict(want_obs=True) if args.mode == "obs" else {}
 for t in range(300):
     env.step(acts[t % len(acts)], **kw)
