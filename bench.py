@@ -387,9 +387,22 @@ def run_ours(args):
             threads = os.cpu_count() or 1
             v, s, dt = cpu_steps_per_s(1 << 18, args.cpu_seconds, threads)
             v1, s1, dt1 = cpu_steps_per_s(1 << 16, min(3.0, args.cpu_seconds), 1)
+            import random as _random
+            from oracle import py_oracle as _py
+            zz = __import__("numpy").load(os.path.join(ROOT, "tests", "golden", "default_map.npz"))
+            pw = _py.World(zz["passable"].astype(bool).tolist(), zz["ports"].tolist(), zz["stock_fuel"].tolist(),
+                           zz["stock_cargo"].tolist())
+            _random.seed(0)
+            tp = time.perf_counter()
+            npy = _py.random_policy_loop(pw, _random, 300_000)
+            py_rate = npy / (time.perf_counter() - tp)
             line["cpu_baseline"] = {
                 "value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                 "single_thread_value": v1,
+                "python_loop_value_per_core": py_rate,
+                "python_loop_what": "oracle/py_oracle.py: the reference's sample_action+step loop (BASELINE configs[0]) as "
+                                    "a scalar pure-Python loop on one core, stdlib random; the reference itself measured "
+                                    "6.2e4 steps/s/core at survey time (BASELINE.md)",
                 "sample": f"{1 << 18} envs x {s} steps ({dt:.1f} s) of the same workload with oracle/shipenv_oracle.c "
                           f"on {threads} threads; the reference itself is pure Python (~6e4 steps/s/core, BASELINE.md)"}
         print(json.dumps(line), flush=True)
