@@ -494,7 +494,10 @@ constexpr int kDeferCap = 64;   // per-warp deferred-env list; a tile adds at mo
 #endif
 // kPolicy: every action of the launch is SHIPENV_ACT_POLICY (SHIPENV_F_ALL_POLICY); the straight-line case is then
 // `sample_action` choosing a MOVE (word 0) followed by that move (words 1, 2); `actions` is never read.
-template <bool kPolicy>
+// kObs: fused observation rows (utils/preprocessing.py:25-62): lanes that need the general path are resolved on the
+// spot (their row must be final before the tile's TMA bulk store), heads go to a shared [256, 6+4P] tile whose
+// constant port tail is written once, one bulk store per tile, two tiles in flight.
+template <bool kPolicy, bool kObs>
 __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
@@ -547,6 +550,16 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
     return;
   }
   mbar_wait(&world_bar, 0);
+  float* obs_tile = nullptr;
+  const int width = a.obs_width;
+  if (kObs) {
+    obs_tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(defer_all) + kDeferCap * 4 * (kThreads / 32));
+    for (int b = 0; b < 2; ++b) {
+      float* row = obs_tile + (size_t(b) * kThreads + tid) * width;
+      for (int c = 6; c < width; ++c) row[c] = w.h->obs_tail[c - 6];
+    }
+  }
+  int obs_buf = 0;
   // ---- consumers ----
   // Everything the streaming loop touches in shared memory is addressed through 32-bit shared
   // addresses computed once (ld.shared with immediate offsets, no generic-address arithmetic).
@@ -590,6 +603,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       st = (st + 1u) & uint32_t(kStages - 1);
       parity ^= uint32_t(st == 0u);
 
+      uint4 fin = rec;               // kObs: the record the observation row is built from
       const uint32_t x = rec.x & 255u, y = (rec.x >> 8) & 255u, dest = rec.x >> 24;
       // Philox block 0 of the (env, clock) cell.  Explicit action: words 0,1 = fuel-cost and cargo-loss draws,
       // 2,3 = reset draws.  Policy: word 0 = choice([N,E,S,W]) (:165-167), 1,2 = the move's draws.
@@ -651,15 +665,35 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
           a.clock[i] = c_out;
         }
         if (!general) a.io.reward_f32[i] = ok ? r : 0.f;
+        if (kObs) fin = ok ? out : rec;
       }
-      const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, ok && no_fuel);
-      const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, ok && do_reset);
-      const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, off_map);
       const uint32_t gen_w = __ballot_sync(0xFFFFFFFFu, general);
-      if (lane < 3) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
-      if (gen_w) {
+      uint32_t gflags = 0;
+      if (kObs) {
+        if (gen_w && general) {        // resolve now: the observation row of this tile must be final
+          gflags = step_general_inline(a, smem, i);
+          fin = a.ships[i];
+        }
+      } else if (gen_w) {
         if (general) defer[n_defer + __popc(gen_w & ((1u << lane) - 1u))] = i;
         n_defer += __popc(gen_w);
+      }
+      const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, (ok && no_fuel) || (gflags & kFlagDone));
+      const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, (ok && do_reset) || (gflags & kFlagReset));
+      const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, off_map || (gflags & kFlagError));
+      if (lane < 3) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
+      if (kObs) {
+        float* tile_base = obs_tile + size_t(obs_buf) * kThreads * width;
+        obs_head(unpack(fin), tile_base + size_t(tid) * width);
+        fence_proxy_async();
+        consumer_sync();
+        if (tid == 0) {
+          tma_store_bulk(a.io.obs + size_t(tile) * kThreads * width, tile_base, uint32_t(kThreads) * uint32_t(width) * 4u);
+          tma_store_commit();
+          tma_store_wait_read<1>();    // the other buffer is free again
+        }
+        obs_buf ^= 1;
+        consumer_sync();
       }
     }
     // ------------------------------ drain the deferred envs, a warp-full at a time ------------------------------
@@ -679,10 +713,16 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       __syncwarp();
     }
   }
+  if (kObs && tid == 0) tma_store_wait_all();
   // the ragged last tile (n % 256 envs) never enters the pipeline: its owner CTA takes the general path for it
   if (full_tiles * kThreads < n && int(blockIdx.x) == full_tiles % int(gridDim.x)) {
     const int i = full_tiles * kThreads + tid;
     const uint32_t f = i < n ? step_general_inline(a, smem, i) : 0u;
+    if (kObs && i < n) {               // the ragged tile's rows are written with plain stores
+      float* row = a.io.obs + size_t(i) * width;
+      obs_head(unpack(a.ships[i]), row);
+      for (int c = 6; c < width; ++c) row[c] = w.h->obs_tail[c - 6];
+    }
     const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, f & kFlagDone);
     const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, f & kFlagReset);
     const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, f & kFlagError);

@@ -73,7 +73,7 @@ struct shipenv_ctx {
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_step_fast, occ_step_fast_policy, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid, occ_mcts;
+  Occ occ_step_fast, occ_step_fast_policy, occ_fast_o, occ_fast_po, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid, occ_mcts;
 };
 
 namespace {
@@ -319,9 +319,32 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   const int64_t tiles = (n + kThreads - 1) / kThreads;
   const bool lean = !a.io.reward_f64 && !a.io.status && !a.io.taken && !a.io.ep_return;
   int grid = 0;
-  if (a.io.obs) {
-    if (!actions) return fail(SHIPENV_E_ARG, "step: the observation variant needs the `actions` array");
-    if (reinterpret_cast<uintptr_t>(a.io.obs) & 15u) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
+  const bool fast_ok = lean && a.io.reward_f32 && a.io.done_bits && a.io.reset_bits && a.io.error_bits && word0 == 0 &&
+                       c->P >= 2 && !c->no_fast_kernel;
+  if (a.io.obs && (reinterpret_cast<uintptr_t>(a.io.obs) & 15u)) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
+  if (fast_ok) {
+    // throughput kernels: step_fast_kernel<policy, obs>
+    size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes + kDeferCap * 4 * (kThreads / 32);
+    if (a.io.obs) smem += 2 * size_t(kThreads) * a.obs_width * 4;
+    void (*kernel)(const StepArgs) = nullptr;
+    shipenv_ctx::Occ* occ = nullptr;
+    if (a.io.obs) { kernel = all_policy ? step_fast_kernel<true, true> : step_fast_kernel<false, true>;
+                    occ = all_policy ? &c->occ_fast_po : &c->occ_fast_o; }
+    else { kernel = all_policy ? step_fast_kernel<true, false> : step_fast_kernel<false, false>;
+           occ = all_policy ? &c->occ_step_fast_policy : &c->occ_step_fast; }
+    if (int rc = grid_for(c, kernel, *occ, kStepBlock, smem, tiles, &grid)) return rc;
+    a.tile_counter = c->d_tile_counter;
+    a.tile_base = c->tile_base;
+    c->tile_base += uint32_t(n / kThreads) + uint32_t(grid);   // every tile once + one failed ticket per CTA
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStepBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this grid's prologue
+    attr[0].val.programmaticStreamSerializationAllowed = 1;            // with the previous grid's tail
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a));
+  } else if (a.io.obs) {
+    if (!actions) return fail(SHIPENV_E_ARG, "step: this output set needs the `actions` array even with SHIPENV_F_ALL_POLICY");
     const size_t base = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + ((kPipeBytes + 127) & ~size_t(127));
     const size_t tile_bytes = size_t(kThreads) * a.obs_width * 4;
     a.obs_bufs = (base + 2 * tile_bytes <= 96 * 1024) ? 2 : 1;
@@ -333,22 +356,6 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
       if (int rc = grid_for(c, step_kernel<true, false>, c->occ_step_obs_full, kStepBlock, smem, tiles, &grid)) return rc;
       step_kernel<true, false><<<grid, kStepBlock, smem, stream>>>(a);
     }
-  } else if (lean && a.io.reward_f32 && a.io.done_bits && a.io.reset_bits && a.io.error_bits && word0 == 0 &&
-             c->P >= 2 && !c->no_fast_kernel) {
-    const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes + kDeferCap * 4 * (kThreads / 32);
-    if (int rc = all_policy ? grid_for(c, step_fast_kernel<true>, c->occ_step_fast_policy, kStepBlock, smem, tiles, &grid)
-                            : grid_for(c, step_fast_kernel<false>, c->occ_step_fast, kStepBlock, smem, tiles, &grid)) return rc;
-    a.tile_counter = c->d_tile_counter;
-    a.tile_base = c->tile_base;
-    c->tile_base += uint32_t(n / kThreads) + uint32_t(grid);   // every tile once + one failed ticket per CTA
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStepBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this grid's prologue
-    attr[0].val.programmaticStreamSerializationAllowed = 1;            // with the previous grid's tail
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (all_policy) CUDA_TRY(cudaLaunchKernelEx(&cfg, step_fast_kernel<true>, a));
-    else CUDA_TRY(cudaLaunchKernelEx(&cfg, step_fast_kernel<false>, a));
   } else {
     if (!actions) return fail(SHIPENV_E_ARG, "step: this output set needs the `actions` array even with SHIPENV_F_ALL_POLICY");
     const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes;
