@@ -487,7 +487,23 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_STEP_MIN_BLOCKS) step_kern
 // shared-memory list; the warp drains the list through step_general OUTSIDE the streaming
 // loop, 32 deferred envs per call, and ORs their done/reset/error bits into the mask words.
 // ------------------------------------------------------------------------------------------
-constexpr int kDeferCap = 64;   // per-warp deferred-env list; a tile adds at most 32
+constexpr int kDeferCap = 64;   // per-warp deferred-env list per env-per-thread; a tile adds at most 32 of each
+
+// kEpt envs per thread: a tile is 256 * kEpt envs; thread t owns envs t, t + 256, ... of the tile.  Two
+// independent env chains per thread interleave (ILP) and share the per-tile bookkeeping.
+template <int kEpt>
+struct alignas(16) FastStage {
+  uint4 ships[kThreads * kEpt];
+  uint32_t clock[kThreads * kEpt];
+  int16_t act[kThreads * kEpt];
+};
+template <int kEpt>
+constexpr size_t fast_smem_bytes() {   // ring slots + full/empty mbarriers + tile ids + deferred lists
+  return sizeof(FastStage<kEpt>) * kStages + 2 * 8 * kStages + 4 * kStages + size_t(kDeferCap) * kEpt * 4 * (kThreads / 32);
+}
+#ifndef SHIPENV_FAST_EPT
+#define SHIPENV_FAST_EPT 1
+#endif
 
 #ifndef SHIPENV_FAST_MIN_BLOCKS
 #define SHIPENV_FAST_MIN_BLOCKS 3
@@ -497,16 +513,20 @@ constexpr int kDeferCap = 64;   // per-warp deferred-env list; a tile adds at mo
 // kObs: fused observation rows (utils/preprocessing.py:25-62): lanes that need the general path are resolved on the
 // spot (their row must be final before the tile's TMA bulk store), heads go to a shared [256, 6+4P] tile whose
 // constant port tail is written once, one bulk store per tile, two tiles in flight.
-template <bool kPolicy, bool kObs>
+template <bool kPolicy, bool kObs, int kEpt>
 __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
   const WorldView w(smem);
   const int tid = threadIdx.x;
   const int n = int(a.n);
-  const int full_tiles = n / kThreads;               // the streaming loop takes complete tiles only
-  TileStage* stage = reinterpret_cast<TileStage*>(smem + ((a.world_bytes + 127u) & ~127u));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage) + sizeof(TileStage) * kStages);
+  static_assert(!kObs || kEpt == 1, "the observation variant keeps one env per thread");
+  constexpr int kTile = kThreads * kEpt;
+  constexpr int kCap = kDeferCap * kEpt;
+  using Stage = FastStage<kEpt>;
+  const int full_tiles = n / kTile;                  // the streaming loop takes complete tiles only
+  Stage* stage = reinterpret_cast<Stage*>(smem + ((a.world_bytes + 127u) & ~127u));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage) + sizeof(Stage) * kStages);
   uint64_t* empty_bar = full_bar + kStages;
   volatile int* stage_tile = reinterpret_cast<volatile int*>(empty_bar + kStages);   // tile index held by each slot
   int* defer_all = const_cast<int*>(stage_tile) + kStages;
@@ -538,12 +558,12 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
           mbar_arrive(&full_bar[st]);
           break;
         }
-        const int base = int(ticket) * kThreads;
+        const int base = int(ticket) * kTile;
         stage_tile[st] = int(ticket);
-        mbar_expect_tx(&full_bar[st], kThreads * (kPolicy ? 20u : 22u));
-        tma_load_bulk(stage[st].ships, a.ships + base, kThreads * 16u, &full_bar[st]);
-        tma_load_bulk(stage[st].clock, a.clock + base, kThreads * 4u, &full_bar[st]);
-        if (!kPolicy) tma_load_bulk(stage[st].act, a.actions + base, kThreads * 2u, &full_bar[st]);
+        mbar_expect_tx(&full_bar[st], kTile * (kPolicy ? 20u : 22u));
+        tma_load_bulk(stage[st].ships, a.ships + base, kTile * 16u, &full_bar[st]);
+        tma_load_bulk(stage[st].clock, a.clock + base, kTile * 4u, &full_bar[st]);
+        if (!kPolicy) tma_load_bulk(stage[st].act, a.actions + base, kTile * 2u, &full_bar[st]);
         ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base;   // in flight while the slot is awaited
       }
     }
@@ -553,7 +573,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   float* obs_tile = nullptr;
   const int width = a.obs_width;
   if (kObs) {
-    obs_tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(defer_all) + kDeferCap * 4 * (kThreads / 32));
+    obs_tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(defer_all) + kCap * 4 * (kThreads / 32));
     for (int b = 0; b < 2; ++b) {
       float* row = obs_tile + (size_t(b) * kThreads + tid) * width;
       for (int c = 6; c < width; ++c) row[c] = w.h->obs_tail[c - 6];
@@ -564,7 +584,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   // Everything the streaming loop touches in shared memory is addressed through 32-bit shared
   // addresses computed once (ld.shared with immediate offsets, no generic-address arithmetic).
   const int lane = tid & 31;
-  int* defer = defer_all + (tid >> 5) * kDeferCap;
+  int* defer = defer_all + (tid >> 5) * kCap;
   int n_defer = 0;                                   // warp-uniform
   const uint32_t wb = smem_u32(smem);                // world blob
   const uint32_t bits_b = wb + uint32_t(sizeof(WorldHdr));
@@ -580,8 +600,8 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   const uint32_t reset_rec_z = uint32_t(__double2loint(w.h->fuel0)), reset_rec_w = uint32_t(__double2hiint(w.h->fuel0));
   const uint32_t stage_b = smem_u32(stage);
   const uint32_t my_ship = stage_b + uint32_t(tid) * 16u;
-  const uint32_t my_clock = stage_b + 4096u + uint32_t(tid) * 4u;
-  const uint32_t my_act = stage_b + 5120u + uint32_t(tid) * 2u;
+  const uint32_t my_clock = stage_b + uint32_t(kTile) * 16u + uint32_t(tid) * 4u;
+  const uint32_t my_act = stage_b + uint32_t(kTile) * 20u + uint32_t(tid) * 2u;
   const uint32_t full_b = smem_u32(full_bar), empty_b = smem_u32(empty_bar);
 
   const uint32_t tile_b = smem_u32(const_cast<int*>(stage_tile));
@@ -589,19 +609,30 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   uint32_t st = 0, parity = 0;                       // next pipeline slot and its phase parity
   while (true) {
     // ------------------------------ streaming loop: no calls in here ------------------------------
-    while (more && n_defer <= kDeferCap - 32) {
+    while (more && n_defer <= kCap - 32 * kEpt) {
       mbar_wait_s(full_b + st * 8u, parity);
       const int tile = int(lds_u32(tile_b + st * 4u));
       if (tile < 0) { more = false; break; }
-      const int i = tile * kThreads + tid;
-      const uint32_t so = st * uint32_t(sizeof(TileStage));
-      const uint4 rec = lds_u4(my_ship + so);
-      const uint32_t c = lds_u32(my_clock + so);
-      const int act = kPolicy ? SHIPENV_ACT_POLICY : lds_s16(my_act + so);
+      const uint32_t so = st * uint32_t(sizeof(Stage));
+      uint4 rec_e[kEpt];
+      uint32_t c_e[kEpt];
+      int act_e[kEpt];
+#pragma unroll
+      for (int e = 0; e < kEpt; ++e) {
+        rec_e[e] = lds_u4(my_ship + so + uint32_t(e) * kThreads * 16u);
+        c_e[e] = lds_u32(my_clock + so + uint32_t(e) * kThreads * 4u);
+        act_e[e] = kPolicy ? SHIPENV_ACT_POLICY : lds_s16(my_act + so + uint32_t(e) * kThreads * 2u);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive_s(empty_b + st * 8u);
       st = (st + 1u) & uint32_t(kStages - 1);
       parity ^= uint32_t(st == 0u);
+#pragma unroll
+      for (int e = 0; e < kEpt; ++e) {
+      const int i = tile * kTile + e * kThreads + tid;
+      const uint4 rec = rec_e[e];
+      const uint32_t c = c_e[e];
+      const int act = act_e[e];
 
       uint4 fin = rec;               // kObs: the record the observation row is built from
       const uint32_t x = rec.x & 255u, y = (rec.x >> 8) & 255u, dest = rec.x >> 24;
@@ -688,13 +719,14 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         fence_proxy_async();
         consumer_sync();
         if (tid == 0) {
-          tma_store_bulk(a.io.obs + size_t(tile) * kThreads * width, tile_base, uint32_t(kThreads) * uint32_t(width) * 4u);
+          tma_store_bulk(a.io.obs + size_t(tile) * kTile * width, tile_base, uint32_t(kThreads) * uint32_t(width) * 4u);
           tma_store_commit();
           tma_store_wait_read<1>();    // the other buffer is free again
         }
         obs_buf ^= 1;
         consumer_sync();
       }
+      }  // envs of this thread
     }
     // ------------------------------ drain the deferred envs, a warp-full at a time ------------------------------
     if (n_defer == 0 && !more) break;
@@ -715,8 +747,11 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   }
   if (kObs && tid == 0) tma_store_wait_all();
   // the ragged last tile (n % 256 envs) never enters the pipeline: its owner CTA takes the general path for it
-  if (full_tiles * kThreads < n && int(blockIdx.x) == full_tiles % int(gridDim.x)) {
-    const int i = full_tiles * kThreads + tid;
+  if (full_tiles * kTile < n && int(blockIdx.x) == full_tiles % int(gridDim.x)) {
+#pragma unroll 1
+    for (int e = 0; e < kEpt; ++e) {
+    const int i = full_tiles * kTile + e * kThreads + tid;
+    if (i - lane >= n) break;          // warp-uniform
     const uint32_t f = i < n ? step_general_inline(a, smem, i) : 0u;
     if (kObs && i < n) {               // the ragged tile's rows are written with plain stores
       float* row = a.io.obs + size_t(i) * width;
@@ -726,7 +761,8 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
     const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, f & kFlagDone);
     const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, f & kFlagReset);
     const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, f & kFlagError);
-    if (lane < 3 && i - lane < n) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
+    if (lane < 3) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
+    }
   }
 }
 

@@ -324,18 +324,20 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   if (a.io.obs && (reinterpret_cast<uintptr_t>(a.io.obs) & 15u)) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
   if (fast_ok) {
     // throughput kernels: step_fast_kernel<policy, obs>
-    size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + kPipeBytes + kDeferCap * 4 * (kThreads / 32);
+    constexpr int kEpt = SHIPENV_FAST_EPT;
+    const int ept = a.io.obs ? 1 : kEpt;
+    size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + (a.io.obs ? fast_smem_bytes<1>() : fast_smem_bytes<kEpt>());
     if (a.io.obs) smem += 2 * size_t(kThreads) * a.obs_width * 4;
     void (*kernel)(const StepArgs) = nullptr;
     shipenv_ctx::Occ* occ = nullptr;
-    if (a.io.obs) { kernel = all_policy ? step_fast_kernel<true, true> : step_fast_kernel<false, true>;
+    if (a.io.obs) { kernel = all_policy ? step_fast_kernel<true, true, 1> : step_fast_kernel<false, true, 1>;
                     occ = all_policy ? &c->occ_fast_po : &c->occ_fast_o; }
-    else { kernel = all_policy ? step_fast_kernel<true, false> : step_fast_kernel<false, false>;
+    else { kernel = all_policy ? step_fast_kernel<true, false, kEpt> : step_fast_kernel<false, false, kEpt>;
            occ = all_policy ? &c->occ_step_fast_policy : &c->occ_step_fast; }
-    if (int rc = grid_for(c, kernel, *occ, kStepBlock, smem, tiles, &grid)) return rc;
+    const int64_t fast_tiles = (n + int64_t(kThreads) * ept - 1) / (int64_t(kThreads) * ept);
+    if (int rc = grid_for(c, kernel, *occ, kStepBlock, smem, fast_tiles, &grid)) return rc;
     a.tile_counter = c->d_tile_counter;
     a.tile_base = c->tile_base;
-    c->tile_base += uint32_t(n / kThreads) + uint32_t(grid);   // every tile once + one failed ticket per CTA
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStepBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -343,6 +345,8 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // with the previous grid's tail
     cfg.attrs = attr; cfg.numAttrs = 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a));
+    // tickets this launch consumes: every complete tile once + one failed ticket per CTA
+    c->tile_base += uint32_t(n / (int64_t(kThreads) * ept)) + uint32_t(grid);
   } else if (a.io.obs) {
     if (!actions) return fail(SHIPENV_E_ARG, "step: this output set needs the `actions` array even with SHIPENV_F_ALL_POLICY");
     const size_t base = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + ((kPipeBytes + 127) & ~size_t(127));
