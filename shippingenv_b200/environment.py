@@ -273,28 +273,30 @@ class Environment:
         return self._build_state(), reward, done, {}
 
     # ------------------------------------------------------------------ rendering (host, cv2; not on the hot path)
+    _PALETTE = ((Entity.WATER, Color.WATER), (Entity.GROUND, Color.GROUND), (Entity.PORT, Color.PORT),
+                (Entity.DESTINY_PORT, Color.DESTINY_PORT), (Entity.TRAVEL, Color.TRAVEL))
+    # the boat sprite of the reference renderer as (row offsets, column offsets, colour)
+    _SPRITE = (((0, 1), (-3, 3), Color.BOAT), ((1, 2), (-2, 2), Color.BOAT), ((-4, 0), (0, 1), Color.BLACK),
+               ((-4, -1), (1, 2), Color.WHITE), ((-3, -2), (2, 3), Color.WHITE))
+
     def render_real_time(self, render_size=(355, 533)):
+        """Same picture as the reference's renderer (shipping/environment.py:106-143), drawn on the host."""
         import cv2
-        g = self.np_game
-        img = np.zeros((g.shape[0], g.shape[1], 3), dtype="uint8")
-        for code, color in ((Entity.WATER, Color.WATER), (Entity.GROUND, Color.GROUND), (Entity.PORT, Color.PORT),
-                            (Entity.DESTINY_PORT, Color.DESTINY_PORT), (Entity.TRAVEL, Color.TRAVEL)):
-            img[g == code] = color
-        bx, by = np.where(g == Entity.BOAT)
-        if len(bx) > 0:
-            x, y = bx[0], by[0]
-            img[x, y - 3:y + 3, :] = Color.BOAT
-            img[x + 1, y - 2:y + 2, :] = Color.BOAT
-            img[x - 4:x, y, :] = Color.BLACK
-            img[x - 4:x - 1, y + 1, :] = Color.WHITE
-            img[x - 3, y + 2, :] = Color.WHITE
-        frame = cv2.resize(img, render_size, interpolation=cv2.INTER_AREA)
-        font = cv2.FONT_HERSHEY_SIMPLEX
-        cv2.putText(frame, f"Fuel: {self.fuel:.2f}", (10, 20), font, 0.5, (255, 255, 255), 1, cv2.LINE_AA)
-        cv2.putText(frame, f"Cargo: {self.cargo}", (10, 40), font, 0.5, (255, 255, 255), 1, cv2.LINE_AA)
-        for idx in range(len(self.port_positions)):
-            cv2.putText(frame, f"P{idx + 1} - Cargo: {self.port_cargo[idx]} - Fuel: {self.port_fuel[idx]}",
-                        (10, 80 + 20 * idx), font, 0.5, (255, 255, 255), 1, cv2.LINE_AA)
+        grid = self.np_game
+        canvas = np.zeros(grid.shape + (3,), dtype=np.uint8)
+        for code, bgr in self._PALETTE:
+            canvas[grid == code] = bgr
+        boats = np.argwhere(grid == Entity.BOAT)
+        if len(boats):
+            bx, by = (int(v) for v in boats[0])
+            for (r0, r1), (c0, c1), bgr in self._SPRITE:
+                canvas[bx + r0:bx + r1, by + c0:by + c1] = bgr
+        frame = cv2.resize(canvas, render_size, interpolation=cv2.INTER_AREA)
+        lines = [(20, f"Fuel: {self.fuel:.2f}"), (40, f"Cargo: {self.cargo}")]
+        lines += [(80 + 20 * k, f"P{k + 1} - Cargo: {c} - Fuel: {f}")
+                  for k, (c, f) in enumerate(zip(self.port_cargo, self.port_fuel))]
+        for ypix, text in lines:
+            cv2.putText(frame, text, (10, ypix), cv2.FONT_HERSHEY_SIMPLEX, 0.5, (255, 255, 255), 1, cv2.LINE_AA)
         cv2.imshow("Environment", frame)
         if cv2.waitKey(100) == ord("q"):
             cv2.destroyAllWindows()
