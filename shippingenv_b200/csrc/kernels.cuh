@@ -56,7 +56,8 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity)
       "DONES_%=:\n"
       "}\n" ::"r"(bar_saddr), "r"(parity) : "memory");
 }
-// producer-side wait: sleeps between polls so that the waiting warp does not eat issue slots
+// producer-side wait: sleeps ~1 us between polls (a tile takes a CTA about that long and kStages tiles are
+// buffered) so that the waiting warp does not eat issue slots
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -64,7 +65,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
       "WAITB_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONEB_%=;\n"
-      "nanosleep.u32 256;\n"
+      "nanosleep.u32 1024;\n"
       "bra WAITB_%=;\n"
       "DONEB_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -115,6 +116,10 @@ __device__ __forceinline__ void tma_store_bulk(void* gmem_dst, const void* smem_
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
                "r"(bytes)
                : "memory");
+}
+// pull a contiguous global range towards L2 (bytes % 16 == 0, 16-B aligned)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int kPending>
@@ -543,13 +548,22 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   }
   // Programmatic dependent launch: let the next step's grid start its prologue while this one runs, and
   // do not touch ships / clock / tickets before the previous grid has completed and flushed its stores.
+  // The CTA's first tile is its block index (no ticket needed); pulling it towards L2 before the wait is only a
+  // hint -- L2 stays coherent with the stores the previous grid may still be making to those lines.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == kThreads && int(blockIdx.x) < full_tiles) {
+    const size_t base = size_t(blockIdx.x) * kTile;
+    tma_prefetch_l2(a.ships + base, kTile * 16u);
+    tma_prefetch_l2(a.clock + base, kTile * 4u);
+    if (!kPolicy) tma_prefetch_l2(a.actions + base, kTile * 2u);
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid >= kThreads) {             // ---- producer warp: lane 0 streams tiles in with TMA ----
     if (tid == kThreads) {
       // Tiles are handed out by a global ticket counter, so SMs that run ahead simply take more tiles
       // (no tail imbalance).  The counter is never reset: the host passes the ticket this launch starts at.
-      uint32_t ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base;
+      // tickets 0..grid-1 are the block indices; later ones come from the counter (offset by the grid size)
+      uint32_t ticket = blockIdx.x;
       for (int it = 0;; ++it) {
         const int st = it % kStages;
         if (it >= kStages) mbar_wait_backoff(&empty_bar[st], uint32_t(it / kStages - 1) & 1u);
@@ -564,7 +578,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         tma_load_bulk(stage[st].ships, a.ships + base, kTile * 16u, &full_bar[st]);
         tma_load_bulk(stage[st].clock, a.clock + base, kTile * 4u, &full_bar[st]);
         if (!kPolicy) tma_load_bulk(stage[st].act, a.actions + base, kTile * 2u, &full_bar[st]);
-        ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base;   // in flight while the slot is awaited
+        ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base + gridDim.x;   // in flight while the slot is awaited
       }
     }
     return;
@@ -596,6 +610,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   const uint32_t id_lo = uint32_t(a.env_id_base), id_hi = uint32_t(a.env_id_base >> 32);
   // lanes 0..2 each own one mask array: one predicated store writes the warp's three ballot words
   uint32_t* const mask_ptr = lane == 0 ? a.io.done_bits : lane == 1 ? a.io.reset_bits : a.io.error_bits;
+  const bool mask_lane = lane < 3;
   const uint32_t reset_rec_y = uint32_t(w.h->cargo0);
   const uint32_t reset_rec_z = uint32_t(__double2loint(w.h->fuel0)), reset_rec_w = uint32_t(__double2hiint(w.h->fuel0));
   const uint32_t stage_b = smem_u32(stage);
@@ -712,7 +727,12 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, (ok && no_fuel) || (gflags & kFlagDone));
       const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, (ok && do_reset) || (gflags & kFlagReset));
       const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, off_map || (gflags & kFlagError));
-      if (lane < 3) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
+      {
+        const uint32_t mask_v = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
+        uint32_t* const mp = mask_ptr + (i >> 5);
+        asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.global.u32 [%0], %1;\n}\n"
+                     :: "l"(mp), "r"(mask_v), "r"(uint32_t(mask_lane)) : "memory");
+      }
       if (kObs) {
         float* tile_base = obs_tile + size_t(obs_buf) * kThreads * width;
         obs_head(unpack(fin), tile_base + size_t(tid) * width);

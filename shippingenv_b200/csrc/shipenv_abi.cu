@@ -345,8 +345,12 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // with the previous grid's tail
     cfg.attrs = attr; cfg.numAttrs = 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a));
-    // tickets this launch consumes: every complete tile once + one failed ticket per CTA
-    c->tile_base += uint32_t(n / (int64_t(kThreads) * ept)) + uint32_t(grid);
+    // counter tickets this launch consumes: one per tile-or-end-marker a CTA fetches after its first (static) tile
+    {
+      const uint32_t full = uint32_t(n / (int64_t(kThreads) * ept));
+      const uint32_t starters = full < uint32_t(grid) ? full : uint32_t(grid);   // CTAs whose first tile exists
+      c->tile_base += (full - starters) + starters;   // every remaining tile once + one failed fetch per started CTA
+    }
   } else if (a.io.obs) {
     if (!actions) return fail(SHIPENV_E_ARG, "step: this output set needs the `actions` array even with SHIPENV_F_ALL_POLICY");
     const size_t base = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + ((kPipeBytes + 127) & ~size_t(127));
