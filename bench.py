@@ -97,6 +97,24 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def pin_to_gpu_numa_node(index):
+    """Restrict this rank to the CPUs NVML reports as local to GPU `index` (first-touch then places its pinned
+    host buffers on that NUMA node).  Returns the number of CPUs kept, or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU side: the oracle port on host threads (ctypes releases the GIL inside the C call)
 # ---------------------------------------------------------------------------------------------
@@ -215,6 +233,8 @@ def run_ours(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = pin_to_gpu_numa_node(local)     # pinned host buffers of the e2e leg land next to the GPU's PCIe root
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__ as entry
@@ -378,12 +398,13 @@ def run_ours(args):
                     "what": "shipenv_step via BatchedEnvironment.step: int16 actions from pinned host memory, f32 reward "
                             "+ done/reset masks to pinned host memory; one stream per env group so that copies "
                             "overlap kernels"},
-            "gpu_launches": launches, "clocks": clocks.summary(),
+            "gpu_launches": launches, "clocks": clocks.summary(), "cpus_pinned_to_gpu_numa_node": numa,
             "rejected_actions_last_step": err, "reward_checksum": checksum,
         }
         if extras:
             line["extras"] = extras
         if world_size == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)          # the CPU baseline uses every host core again
             threads = os.cpu_count() or 1
             v, s, dt = cpu_steps_per_s(1 << 18, args.cpu_seconds, threads)
             v1, s1, dt1 = cpu_steps_per_s(1 << 16, min(3.0, args.cpu_seconds), 1)
