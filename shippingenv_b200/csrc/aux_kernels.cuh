@@ -1,0 +1,166 @@
+// aux_kernels.cuh -- reset, observe, sample_action, valid-action mask, discretize_state keys.
+#pragma once
+#include "pipeline.cuh"
+
+namespace shipenv {
+
+// ------------------------------------------------------------------------------------------
+// reset / observe / sample_action
+// ------------------------------------------------------------------------------------------
+struct ResetArgs {
+  const void* world; uint32_t world_bytes;
+  uint4* ships; uint32_t* clock; const uint32_t* mask_bits;
+  uint64_t seed, env_id_base; int64_t n;
+  uint32_t round_key[20];
+};
+
+__global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__ ResetArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t world_bar;
+  stage_world(smem, a.world, a.world_bytes, &world_bar);
+  const WorldView w(smem);
+  const int64_t n_tiles = (a.n + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i = tile * kThreads + threadIdx.x;
+    if (i >= a.n) continue;
+    if (a.mask_bits && !((a.mask_bits[i >> 5] >> (i & 31)) & 1u)) continue;
+    const uint32_t c = a.clock[i];
+    ShipR s;
+    Rng g;
+    g.seek(a.round_key, c, a.env_id_base + uint64_t(i), 0u);
+    env_reset(w, s, g);
+    st_stream_u4(a.ships + i, pack(s));
+    a.clock[i] = ((c >> 16) + 1u) << 16;
+  }
+}
+
+struct ObserveArgs {
+  const void* world; uint32_t world_bytes;
+  const uint4* ships; float* obs; int64_t n; int obs_width;
+};
+
+__global__ void __launch_bounds__(kThreads) observe_kernel(const ObserveArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t world_bar;
+  stage_world(smem, a.world, a.world_bytes, &world_bar);
+  const WorldView w(smem);
+  const int width = a.obs_width, tid = threadIdx.x;
+  float* tile = reinterpret_cast<float*>(smem + ((a.world_bytes + 127u) & ~127u));
+  for (int c = 6; c < width; ++c) tile[size_t(tid) * width + c] = w.h->obs_tail[c - 6];
+  const int64_t n_tiles = (a.n + kThreads - 1) / kThreads;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t i = t * kThreads + tid;
+    if (tid == 0) tma_store_wait_read<0>();
+    __syncthreads();
+    if (i < a.n) obs_head(unpack(a.ships[i]), tile + size_t(tid) * width);
+    fence_proxy_async();
+    __syncthreads();
+    const int64_t row0 = t * kThreads;
+    const int rows = int(min(int64_t(kThreads), a.n - row0));
+    float* gdst = a.obs + row0 * width;
+    const uint32_t bytes = uint32_t(rows) * uint32_t(width) * 4u;
+    if ((bytes & 15u) == 0) {
+      if (tid == 0) { tma_store_bulk(gdst, tile, bytes); tma_store_commit(); }
+    } else {
+      for (int j = tid; j < rows * width; j += kThreads) gdst[j] = tile[j];
+      __syncthreads();
+    }
+  }
+  if (tid == 0) tma_store_wait_all();
+}
+
+struct SampleArgs {
+  const void* world; uint32_t world_bytes;
+  const uint4* ships; const uint32_t* clock;
+  int16_t* actions; uint8_t* words_used; uint8_t* status;
+  uint64_t seed, env_id_base; int64_t n; uint32_t word0;
+  uint32_t round_key[20];
+};
+
+__global__ void __launch_bounds__(kThreads) sample_kernel(const __grid_constant__ SampleArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t world_bar;
+  stage_world(smem, a.world, a.world_bytes, &world_bar);
+  const WorldView w(smem);
+  const int64_t n_tiles = (a.n + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i = tile * kThreads + threadIdx.x;
+    if (i >= a.n) continue;
+    const ShipR s = unpack(a.ships[i]);
+    Rng g;
+    g.seek(a.round_key, a.clock[i], a.env_id_base + uint64_t(i), a.word0);
+    int cat = kCatJunk, val = 0;
+    int st = w.h->P == 0 ? SHIPENV_ST_NO_PORTS : sample_action(w, s, g, cat, val);
+    a.actions[i] = st == SHIPENV_ST_OK ? int16_t(encode_action(cat, val, w.h->P)) : int16_t(-2);
+    if (a.words_used) a.words_used[i] = uint8_t(g.i - a.word0);
+    if (a.status) a.status[i] = uint8_t(st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// DQN valid-action mask (agents/dqn.py:125-175), one env per thread, ceil(A/32) words per env
+// ------------------------------------------------------------------------------------------
+struct ValidArgs {
+  const void* world; uint32_t world_bytes;
+  const uint4* ships; uint32_t* mask; int64_t n; int words;
+};
+
+// bits [lo, hi) of a bit string, restricted to word `wi`
+__device__ __forceinline__ uint32_t range_bits(int lo, int hi, int wi) {
+  const int a = max(lo - wi * 32, 0), b = min(hi - wi * 32, 32);
+  if (a >= b) return 0u;
+  return (b == 32 ? 0xFFFFFFFFu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
+}
+
+__global__ void __launch_bounds__(kThreads) valid_actions_kernel(const ValidArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t world_bar;
+  stage_world(smem, a.world, a.world_bytes, &world_bar);
+  const WorldView w(smem);
+  const int P = w.h->P;
+  const int64_t n_tiles = (a.n + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i = tile * kThreads + threadIdx.x;
+    if (i >= a.n) continue;
+    const ShipR s = unpack(a.ships[i]);
+    const uint32_t key = uint32_t(s.x) | (uint32_t(s.y) << 8);
+    uint32_t select = 0;                              // bit k: port k selectable (:141-156)
+    for (int k = 0; k < P; ++k)
+      if (k != s.origin && (w.h->port[k] & 0xFFFFu) == key) select |= 1u << k;
+    const int cur = current_port(w, s);                // :159-173
+    const int n_cargo = cur >= 0 ? min(int(w.h->port[cur] >> 24), SHIPENV_N_CARGO_ACTIONS - 1) : 0;
+    const int n_fuel = cur >= 0 ? min(int((w.h->port[cur] >> 16) & 255u), SHIPENV_N_FUEL_ACTIONS - 1) : 0;
+    const int c0 = 4 + P + 1, f0 = 4 + P + SHIPENV_N_CARGO_ACTIONS + 1;   // first amount is 1
+    for (int wi = 0; wi < a.words; ++wi) {
+      uint32_t m = range_bits(0, 4, wi);               // the four moves are always valid (:137-139)
+      m |= range_bits(c0, c0 + n_cargo, wi) | range_bits(f0, f0 + n_fuel, wi);
+      for (int k = 0; k < P; ++k)
+        if ((select >> k) & 1u) m |= range_bits(4 + k, 5 + k, wi);
+      a.mask[i * a.words + wi] = m;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// discretize_state (utils/preprocessing.py:65-90): six int16 per env, no world needed
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bucket(double v, double width) {   // min(int(v / width), 4), int() truncates
+  const double q = __ddiv_rn(v, width);
+  const int b = q >= 2147483520.0 ? 2147483647 : q <= -2147483520.0 ? -2147483647 : __double2int_rz(q);
+  return max(min(b, 4), -32768);
+}
+
+__global__ void __launch_bounds__(kThreads) discretize_kernel(const uint4* __restrict__ ships, int16_t* __restrict__ keys,
+                                                              int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kThreads) {
+    const ShipR s = unpack(ships[i]);
+    int16_t* k = keys + i * 6;
+    k[0] = int16_t(s.x); k[1] = int16_t(s.y);
+    k[2] = int16_t(bucket(s.fuel, 10.0));      // the state dict's "cargo" is fuel (shipping/environment.py:206)
+    k[3] = int16_t(bucket(s.fuel, 20.0));
+    k[4] = s.origin == kNone ? int16_t(-1) : int16_t(s.origin);
+    k[5] = s.dest == kNone ? int16_t(-1) : int16_t(s.dest);
+  }
+}
+
+}  // namespace shipenv

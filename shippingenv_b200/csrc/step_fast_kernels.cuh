@@ -1,0 +1,311 @@
+// step_fast_kernels.cuh -- the throughput kernels (reward_f32 + masks, optional fused observation rows,
+// optional all-policy mode): the kernel bench.py measures.
+#pragma once
+#include "step_kernels.cuh"
+
+namespace shipenv {
+
+// ------------------------------------------------------------------------------------------
+// step, throughput specialisation: reward_f32 + the three masks only, word0 == 0, P >= 2.
+//
+// Same TMA producer / consumer pipeline as step_kernel, but the streaming loop contains the
+// straight-line MOVE case only.  Lanes that need anything else (non-move action, cargo-loss
+// draw, arrival, destination re-draw, unset destination) push their env index on a per-warp
+// shared-memory list; the warp drains the list through step_general OUTSIDE the streaming
+// loop, 32 deferred envs per call, and ORs their done/reset/error bits into the mask words.
+// ------------------------------------------------------------------------------------------
+constexpr int kDeferCap = 64;   // per-warp deferred-env list per env-per-thread; a tile adds at most 32 of each
+
+// kEpt envs per thread: a tile is 256 * kEpt envs; thread t owns envs t, t + 256, ... of the tile.  Two
+// independent env chains per thread interleave (ILP) and share the per-tile bookkeeping.
+template <int kEpt>
+struct alignas(16) FastStage {
+  uint4 ships[kThreads * kEpt];
+  uint32_t clock[kThreads * kEpt];
+  int16_t act[kThreads * kEpt];
+};
+template <int kEpt>
+constexpr size_t fast_smem_bytes() {   // ring slots + full/empty mbarriers + tile ids + deferred lists
+  return sizeof(FastStage<kEpt>) * kStages + 2 * 8 * kStages + 4 * kStages + size_t(kDeferCap) * kEpt * 4 * (kThreads / 32);
+}
+#ifndef SHIPENV_FAST_EPT
+#define SHIPENV_FAST_EPT 1
+#endif
+
+#ifndef SHIPENV_FAST_MIN_BLOCKS
+#define SHIPENV_FAST_MIN_BLOCKS 3
+#endif
+// kPolicy: every action of the launch is SHIPENV_ACT_POLICY (SHIPENV_F_ALL_POLICY); the straight-line case is then
+// `sample_action` choosing a MOVE (word 0) followed by that move (words 1, 2); `actions` is never read.
+// kObs: fused observation rows (utils/preprocessing.py:25-62): lanes that need the general path are resolved on the
+// spot (their row must be final before the tile's TMA bulk store), heads go to a shared [256, 6+4P] tile whose
+// constant port tail is written once, one bulk store per tile, two tiles in flight.
+template <bool kPolicy, bool kObs, int kEpt>
+__global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast_kernel(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t world_bar;
+  const WorldView w(smem);
+  const int tid = threadIdx.x;
+  const int n = int(a.n);
+  static_assert(!kObs || kEpt == 1, "the observation variant keeps one env per thread");
+  constexpr int kTile = kThreads * kEpt;
+  constexpr int kCap = kDeferCap * kEpt;
+  using Stage = FastStage<kEpt>;
+  const int full_tiles = n / kTile;                  // the streaming loop takes complete tiles only
+  Stage* stage = reinterpret_cast<Stage*>(smem + ((a.world_bytes + 127u) & ~127u));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage) + sizeof(Stage) * kStages);
+  uint64_t* empty_bar = full_bar + kStages;
+  volatile int* stage_tile = reinterpret_cast<volatile int*>(empty_bar + kStages);   // tile index held by each slot
+  int* defer_all = const_cast<int*>(stage_tile) + kStages;
+  if (tid == 0) {
+    mbar_init(&world_bar, 1);
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], kThreads / 32); }
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {                    // the world blob and the first tiles are fetched concurrently
+    mbar_expect_tx(&world_bar, a.world_bytes);
+    tma_load_bulk(smem, a.world, a.world_bytes, &world_bar);
+  }
+  // Programmatic dependent launch: let the next step's grid start its prologue while this one runs, and
+  // do not touch ships / clock / tickets before the previous grid has completed and flushed its stores.
+  // The CTA's first tile is its block index (no ticket needed); pulling it towards L2 before the wait is only a
+  // hint -- L2 stays coherent with the stores the previous grid may still be making to those lines.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == kThreads && int(blockIdx.x) < full_tiles) {
+    const size_t base = size_t(blockIdx.x) * kTile;
+    tma_prefetch_l2(a.ships + base, kTile * 16u);
+    tma_prefetch_l2(a.clock + base, kTile * 4u);
+    if (!kPolicy) tma_prefetch_l2(a.actions + base, kTile * 2u);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tid >= kThreads) {             // ---- producer warp: lane 0 streams tiles in with TMA ----
+    if (tid == kThreads) {
+      // Tiles are handed out by a global ticket counter, so SMs that run ahead simply take more tiles
+      // (no tail imbalance).  The counter is never reset: the host passes the ticket this launch starts at.
+      // tickets 0..grid-1 are the block indices; later ones come from the counter (offset by the grid size)
+      uint32_t ticket = blockIdx.x;
+      for (int it = 0;; ++it) {
+        const int st = it % kStages;
+        if (it >= kStages) mbar_wait_backoff(&empty_bar[st], uint32_t(it / kStages - 1) & 1u);
+        if (ticket >= uint32_t(full_tiles)) {          // out of tiles: publish the end marker
+          stage_tile[st] = -1;
+          mbar_arrive(&full_bar[st]);
+          break;
+        }
+        const int base = int(ticket) * kTile;
+        stage_tile[st] = int(ticket);
+        mbar_expect_tx(&full_bar[st], kTile * (kPolicy ? 20u : 22u));
+        tma_load_bulk(stage[st].ships, a.ships + base, kTile * 16u, &full_bar[st]);
+        tma_load_bulk(stage[st].clock, a.clock + base, kTile * 4u, &full_bar[st]);
+        if (!kPolicy) tma_load_bulk(stage[st].act, a.actions + base, kTile * 2u, &full_bar[st]);
+        ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base + gridDim.x;   // in flight while the slot is awaited
+      }
+    }
+    return;
+  }
+  mbar_wait(&world_bar, 0);
+  float* obs_tile = nullptr;
+  const int width = a.obs_width;
+  if (kObs) {
+    obs_tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(defer_all) + kCap * 4 * (kThreads / 32));
+    for (int b = 0; b < 2; ++b) {
+      float* row = obs_tile + (size_t(b) * kThreads + tid) * width;
+      for (int c = 6; c < width; ++c) row[c] = w.h->obs_tail[c - 6];
+    }
+  }
+  int obs_buf = 0;
+  // ---- consumers ----
+  // Everything the streaming loop touches in shared memory is addressed through 32-bit shared
+  // addresses computed once (ld.shared with immediate offsets, no generic-address arithmetic).
+  const int lane = tid & 31;
+  int* defer = defer_all + (tid >> 5) * kCap;
+  int n_defer = 0;                                   // warp-uniform
+  const uint32_t wb = smem_u32(smem);                // world blob
+  const uint32_t bits_b = wb + uint32_t(sizeof(WorldHdr));
+  const uint32_t W = uint32_t(w.h->W), H = uint32_t(w.h->H), P = uint32_t(w.h->P);
+  const uint32_t cap = uint32_t(w.h->capacity);
+  const uint32_t wpr = uint32_t(w.h->wpr);
+  const bool auto_reset = a.flags & SHIPENV_F_AUTO_RESET;
+  const uint32_t trunc_at = a.max_steps > 0 ? uint32_t(a.max_steps) : 0x10000u;   // never reached when disabled
+  const uint32_t id_lo = uint32_t(a.env_id_base), id_hi = uint32_t(a.env_id_base >> 32);
+  // lanes 0..2 each own one mask array: one predicated store writes the warp's three ballot words
+  uint32_t* const mask_ptr = lane == 0 ? a.io.done_bits : lane == 1 ? a.io.reset_bits : a.io.error_bits;
+  const bool mask_lane = lane < 3;
+  const uint32_t reset_rec_y = uint32_t(w.h->cargo0);
+  const uint32_t reset_rec_z = uint32_t(__double2loint(w.h->fuel0)), reset_rec_w = uint32_t(__double2hiint(w.h->fuel0));
+  const uint32_t stage_b = smem_u32(stage);
+  const uint32_t my_ship = stage_b + uint32_t(tid) * 16u;
+  const uint32_t my_clock = stage_b + uint32_t(kTile) * 16u + uint32_t(tid) * 4u;
+  const uint32_t my_act = stage_b + uint32_t(kTile) * 20u + uint32_t(tid) * 2u;
+  const uint32_t full_b = smem_u32(full_bar), empty_b = smem_u32(empty_bar);
+
+  const uint32_t tile_b = smem_u32(const_cast<int*>(stage_tile));
+  bool more = true;                                  // warp-uniform: the end marker has not been seen yet
+  uint32_t st = 0, parity = 0;                       // next pipeline slot and its phase parity
+  while (true) {
+    // ------------------------------ streaming loop: no calls in here ------------------------------
+    while (more && n_defer <= kCap - 32 * kEpt) {
+      mbar_wait_s(full_b + st * 8u, parity);
+      const int tile = int(lds_u32(tile_b + st * 4u));
+      if (tile < 0) { more = false; break; }
+      const uint32_t so = st * uint32_t(sizeof(Stage));
+      uint4 rec_e[kEpt];
+      uint32_t c_e[kEpt];
+      int act_e[kEpt];
+#pragma unroll
+      for (int e = 0; e < kEpt; ++e) {
+        rec_e[e] = lds_u4(my_ship + so + uint32_t(e) * kThreads * 16u);
+        c_e[e] = lds_u32(my_clock + so + uint32_t(e) * kThreads * 4u);
+        act_e[e] = kPolicy ? SHIPENV_ACT_POLICY : lds_s16(my_act + so + uint32_t(e) * kThreads * 2u);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_s(empty_b + st * 8u);
+      st = (st + 1u) & uint32_t(kStages - 1);
+      parity ^= uint32_t(st == 0u);
+#pragma unroll
+      for (int e = 0; e < kEpt; ++e) {
+      const int i = tile * kTile + e * kThreads + tid;
+      const uint4 rec = rec_e[e];
+      const uint32_t c = c_e[e];
+      const int act = act_e[e];
+
+      uint4 fin = rec;               // kObs: the record the observation row is built from
+      const uint32_t x = rec.x & 255u, y = (rec.x >> 8) & 255u, dest = rec.x >> 24;
+      // Philox block 0 of the (env, clock) cell.  Explicit action: words 0,1 = fuel-cost and cargo-loss draws,
+      // 2,3 = reset draws.  Policy: word 0 = choice([N,E,S,W]) (:165-167), 1,2 = the move's draws.
+      uint32_t wd[4];
+      {
+        const uint32_t lo = id_lo + uint32_t(i);
+        philox_rk(0u, c, lo, id_hi + uint32_t(lo < id_lo), a.round_key, wd);
+      }
+      const uint32_t w_cost = kPolicy ? wd[1] : wd[0], w_loss = kPolicy ? wd[2] : wd[1];
+      const double fuel = __hiloint2double(int(rec.w), int(rec.z));
+      // N,E,S,W = (0,-1),(-1,0),(0,1),(1,0): odd actions move along x, even ones along y
+      const int m = kPolicy ? int(__umulhi(wd[0], 4u)) : (act & 3);
+      const int dx = (m & 1) * (m - 2), dy = ((m & 1) ^ 1) * (m - 1);
+      const uint32_t nx = x + uint32_t(dx), ny = y + uint32_t(dy);
+      bool is_move;
+      if (kPolicy) {   // sample_action (:245-263) picks a MOVE unless the ship sits on a port with no cargo / no fuel
+        const bool on_port = (lds_u32(bits_b + (uint32_t(w.h->n_bit_words) + x * wpr + (y >> 5)) * 4u) >> (y & 31u)) & 1u;
+        is_move = dest != uint32_t(kNone) && !(on_port && (rec.y == 0u || fuel == 0.0));
+      } else {
+        is_move = unsigned(act) < 4u && dest != uint32_t(kNone);
+      }
+      const bool in_map = nx < W && ny < H;          // unsigned: -1 wraps to a huge value  (:284)
+      const double cost = __dadd_rn(1.0, __dadd_rn(-0.1, __dmul_rn(0.1 - (-0.1), unit_double(w_cost))));   // :103-104
+      const bool no_fuel = fuel < cost;                                                   // :288
+      const uint32_t cell = in_map ? nx * wpr + (ny >> 5) : 0u;
+      const bool water = (lds_u32(bits_b + cell * 4u) >> (ny & 31u)) & 1u;                // :293
+      const uint32_t pd = lds_u32(wb + uint32_t(offsetof(WorldHdr, port)) + (dest & 31u) * 4u);
+      const uint32_t tx = pd & 255u, ty = (pd >> 8) & 255u;
+      // closer <=> d_prev - d_new > 0 <=> (x - tx) * dx + (y - ty) * dy < 0 for a unit move   (:309-312)
+      const bool closer = (int(x) - int(tx)) * dx + (int(y) - int(ty)) * dy < 0;
+      const uint32_t px = water ? nx : x, py = water ? ny : y;
+      // loss_thr[cap] = 0xFFFFFFFF: cargo >= capacity always draws; negative cargo goes the general way
+      const bool trigger = w_loss <= lds_u32(wb + uint32_t(offsetof(WorldHdr, loss_thr)) + min(uint32_t(rec.y), cap) * 4u);  // :318-320
+      const bool arrive = px == tx && py == ty;                                           // :325
+      const uint32_t c1 = c + 1u;
+      const bool do_reset = auto_reset && (no_fuel || (c1 & 0xFFFFu) >= trunc_at);
+      const uint32_t ro = __umulhi(wd[2], P), rd = __umulhi(wd[3], P);                    // :232-233
+      // policy: an off-map choice is re-drawn and a reset needs words 3 and 4 -- both go the general way
+      const bool general = kPolicy ? (!is_move || !in_map || trigger || arrive || do_reset)
+                                   : (!is_move || (in_map && (trigger || arrive || (do_reset && ro == rd))));
+      const bool ok = is_move && in_map && !general;
+      const bool off_map = !kPolicy && is_move && !in_map;
+      {
+        const double fuel1 = water ? __dsub_rn(fuel, cost) : fuel;                        // :298
+        uint4 out;
+        out.x = px | (py << 8) | (rec.x & 0xFFFF0000u);
+        out.y = rec.y;
+        out.z = uint32_t(__double2loint(fuel1)); out.w = uint32_t(__double2hiint(fuel1));
+        uint32_t c_out = c1;
+        if (do_reset) {                                                                   // :227-243
+          out.x = (lds_u32(wb + uint32_t(offsetof(WorldHdr, port)) + ro * 4u) & 0xFFFFu) | (ro << 16) | (rd << 24);
+          out.y = reset_rec_y; out.z = reset_rec_z; out.w = reset_rec_w;
+          c_out = ((c >> 16) + 1u) << 16;
+        }
+        const float r = lds_f32(wb + uint32_t(offsetof(WorldHdr, move_reward_f32)) +
+                                ((uint32_t(no_fuel) << 2) | (uint32_t(!water) << 1) | uint32_t(closer)) * 4u);
+        if (ok) {
+          st_stream_u4(a.ships + i, out);
+          a.clock[i] = c_out;
+        }
+        if (!general) a.io.reward_f32[i] = ok ? r : 0.f;
+        if (kObs) fin = ok ? out : rec;
+      }
+      const uint32_t gen_w = __ballot_sync(0xFFFFFFFFu, general);
+      uint32_t gflags = 0;
+      if (kObs) {
+        if (gen_w && general) {        // resolve now: the observation row of this tile must be final
+          gflags = step_general_inline(a, smem, i);
+          fin = a.ships[i];
+        }
+      } else if (gen_w) {
+        if (general) defer[n_defer + __popc(gen_w & ((1u << lane) - 1u))] = i;
+        n_defer += __popc(gen_w);
+      }
+      const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, (ok && no_fuel) || (gflags & kFlagDone));
+      const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, (ok && do_reset) || (gflags & kFlagReset));
+      const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, off_map || (gflags & kFlagError));
+      {
+        const uint32_t mask_v = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
+        uint32_t* const mp = mask_ptr + (i >> 5);
+        asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.global.u32 [%0], %1;\n}\n"
+                     :: "l"(mp), "r"(mask_v), "r"(uint32_t(mask_lane)) : "memory");
+      }
+      if (kObs) {
+        float* tile_base = obs_tile + size_t(obs_buf) * kThreads * width;
+        obs_head(unpack(fin), tile_base + size_t(tid) * width);
+        fence_proxy_async();
+        consumer_sync();
+        if (tid == 0) {
+          tma_store_bulk(a.io.obs + size_t(tile) * kTile * width, tile_base, uint32_t(kThreads) * uint32_t(width) * 4u);
+          tma_store_commit();
+          tma_store_wait_read<1>();    // the other buffer is free again
+        }
+        obs_buf ^= 1;
+        consumer_sync();
+      }
+      }  // envs of this thread
+    }
+    // ------------------------------ drain the deferred envs, a warp-full at a time ------------------------------
+    if (n_defer == 0 && !more) break;
+    __syncwarp();
+    while (n_defer > 0) {
+      const int k = min(n_defer, 32);
+      if (lane < k) {
+        const int i = defer[n_defer - k + lane];
+        const uint32_t f = step_general_inline(a, smem, i);   // inlined: an ABI call would pin loop state to the stack
+        const uint32_t bit = 1u << (i & 31);
+        if (f & kFlagDone) atomicOr(a.io.done_bits + (i >> 5), bit);
+        if (f & kFlagReset) atomicOr(a.io.reset_bits + (i >> 5), bit);
+        if (f & kFlagError) atomicOr(a.io.error_bits + (i >> 5), bit);
+      }
+      n_defer -= k;
+      __syncwarp();
+    }
+  }
+  if (kObs && tid == 0) tma_store_wait_all();
+  // the ragged last tile (n % 256 envs) never enters the pipeline: its owner CTA takes the general path for it
+  if (full_tiles * kTile < n && int(blockIdx.x) == full_tiles % int(gridDim.x)) {
+#pragma unroll 1
+    for (int e = 0; e < kEpt; ++e) {
+    const int i = full_tiles * kTile + e * kThreads + tid;
+    if (i - lane >= n) break;          // warp-uniform
+    const uint32_t f = i < n ? step_general_inline(a, smem, i) : 0u;
+    if (kObs && i < n) {               // the ragged tile's rows are written with plain stores
+      float* row = a.io.obs + size_t(i) * width;
+      obs_head(unpack(a.ships[i]), row);
+      for (int c = 6; c < width; ++c) row[c] = w.h->obs_tail[c - 6];
+    }
+    const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, f & kFlagDone);
+    const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, f & kFlagReset);
+    const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, f & kFlagError);
+    if (lane < 3) mask_ptr[i >> 5] = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
+    }
+  }
+}
+
+}  // namespace shipenv
