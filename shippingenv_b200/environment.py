@@ -272,6 +272,44 @@ class Environment:
         done = bool(h[_DONE] & 1)
         return self._build_state(), reward, done, {}
 
+    # ------------------------------------------------------------------ extensions: MCTS on the device
+    def _root_tensor(self):
+        self._pack()
+        return self._dev[:16].clone().view(1, 16)
+
+    def rollout_returns(self, simulations=50, max_rollout_steps=100, root_id=None):
+        """``MCTSAgent._rollout`` (agents/mcts.py:211-238) x ``simulations`` from the current state in ONE launch
+        (the reference builds an env copy and loops in Python for each).  Returns a list of floats."""
+        ctx = self._sync_world()
+        roots = self._root_tensor()
+        ret = torch.empty(simulations, dtype=torch.float64, device=self._device)
+        ctx.rollout(roots.data_ptr(), 1, simulations, max_rollout_steps, ret.data_ptr(), None, None, None,
+                    self._seed, self._clock if root_id is None else root_id, self._stream())
+        return ret.cpu().tolist()
+
+    def mcts_action(self, simulations=50, max_rollout_steps=100, c_param=1.4, root_id=None):
+        """``MCTSAgent.choose_action`` (agents/mcts.py:240-292) from the current state in ONE launch: UCB1 tree,
+        expansion, rollouts, backpropagation and the final pick all run on the device.  Returns the action in the
+        environment's format, ``[ActionType.MOVE_SHIP, [dx, dy]]``; falls back to ``sample_action()`` when the tree
+        has no children or the state is not the four-move case, as the reference does (:291-292)."""
+        ctx = self._sync_world()
+        roots = self._root_tensor()
+        dev = self._device
+        act = torch.empty(1, dtype=torch.int16, device=dev)
+        visits = torch.empty(1, dtype=torch.int32, device=dev)
+        ca = torch.empty(4, dtype=torch.int16, device=dev)
+        cv = torch.empty(4, dtype=torch.int32, device=dev)
+        ct = torch.empty(4, dtype=torch.float64, device=dev)
+        st = torch.empty(1, dtype=torch.uint8, device=dev)
+        log_table = np.concatenate([[0.0], np.log(np.arange(1, simulations + 2))])
+        ctx.mcts(roots.data_ptr(), 1, simulations, max_rollout_steps, c_param, log_table.ctypes.data, act.data_ptr(),
+                 visits.data_ptr(), ca.data_ptr(), cv.data_ptr(), ct.data_ptr(), st.data_ptr(), self._seed,
+                 self._clock if root_id is None else root_id, self._stream())
+        a = int(act.item())
+        if a < 0:
+            return self.sample_action()
+        return [ActionType.MOVE_SHIP, list(MOVES[a])]
+
     # ------------------------------------------------------------------ rendering (host, cv2; not on the hot path)
     _PALETTE = ((Entity.WATER, Color.WATER), (Entity.GROUND, Color.GROUND), (Entity.PORT, Color.PORT),
                 (Entity.DESTINY_PORT, Color.DESTINY_PORT), (Entity.TRAVEL, Color.TRAVEL))

@@ -193,3 +193,22 @@ def test_agent_call_patterns(default_map):
                               "Not currently at port", "Move is out of range")
         assert env._build_state()["ship"]["fuel"] == env.fuel
     assert n_ok >= 8        # 4 moves + 4 selectable ports; takes are rejected once the ship left the port
+
+
+def test_facade_mcts_extensions_match_batched_kernels():
+    """Environment.rollout_returns / mcts_action are the R = 1 view of shipenv_rollout / shipenv_mcts."""
+    from shippingenv_b200 import ActionType
+    z = golden("g11_mcts")
+    move = [(0, -1), (-1, 0), (0, 1), (1, 0)]
+    for r in (0, 3, 7, 20):
+        env = make_env(int(z["seed"]))
+        x, y, o, d = (int(v) for v in z["root_pos"][r])
+        env.ship_position, env.origin_port_index, env.destination_port_index = [x, y], o, d
+        env.cargo = int(z["root_cargo"][r])
+        env.fuel = float(np.uint64(z["root_fuel"][r]).view(np.float64))
+        a = env.mcts_action(50, 100, root_id=int(z["root_id_base"]) + r)
+        assert a == [ActionType.MOVE_SHIP, list(move[int(z["action_S50_L100"][r])])]
+        before = (list(env.ship_position), env.fuel, env.cargo, env._clock)
+        rets = env.rollout_returns(6, 25, root_id=1000)
+        assert len(rets) == 6 and len(set(rets)) > 1
+        assert before == (list(env.ship_position), env.fuel, env.cargo, env._clock)   # planning never moves the env
