@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
+  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [8][blockDim.x] words
   const int64_t total = a.R * int64_t(a.S);
   const int64_t n_tiles = (total + kRolloutThreads - 1) / kRolloutThreads;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -31,12 +32,13 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
     const int64_t r = j / a.S;
     const int sim = int(j - r * a.S);
     ShipR s = unpack(__ldg(a.roots + r));
-    Rng g;
-    g.seek(a.round_key, uint32_t(sim), a.root_id_base + uint64_t(r), 0u);
+    RngFifo g;
+    g.seek(a.round_key, fifo + threadIdx.x, blockDim.x, uint32_t(sim), a.root_id_base + uint64_t(r));
     double total_reward = 0.0;                     // agents/mcts.py:224
     bool done = false;
     int steps = 0, st = SHIPENV_ST_OK, fails = 0;
     while (!done && steps < a.L) {                 // agents/mcts.py:228
+      g.ensure();
       if (w.h->P == 0) { st = SHIPENV_ST_NO_PORTS; break; }
       if (s.dest == kNone && current_port(w, s) < 0) { st = SHIPENV_ST_NO_DEST; break; }
       int cat, val;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
+  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [8][blockDim.x] words
   for (int64_t r = blockIdx.x * int64_t(kMctsThreads) + threadIdx.x; r < a.R; r += int64_t(gridDim.x) * kMctsThreads) {
     const ShipR root = unpack(__ldg(a.roots + r));
     MctsTree t;
@@ -119,14 +122,15 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
     t.moves_ok[0] = mcts_moves_ok(root);
     for (int sim = 0; sim < a.S && st == SHIPENV_ST_OK; ++sim) {
       ShipR s = root;                                                        // _create_env_copy, :257
-      Rng g;
-      g.seek(a.round_key, uint32_t(sim), a.root_id_base + uint64_t(r), 0u);
+      RngFifo g;
+      g.seek(a.round_key, fifo + threadIdx.x, blockDim.x, uint32_t(sim), a.root_id_base + uint64_t(r));
       int node = 0;
       bool done = false;
       double rew = 0.0;
       for (;;) {                                                             // selection, :260-268
         if (!t.moves_ok[node]) { st = SHIPENV_ST_MCTS_UNSUPPORTED; break; }
         if (t.nchild[node] != 4) break;
+        g.ensure();
         node = mcts_best_child(t, node, a.c_param, a.log_table);
         const int e = do_action(w, s, g, kCatMove, t.action[node], rew, done);
         if (e != SHIPENV_ST_OK || done) break;
@@ -137,6 +141,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
       for (int k = 0; k < t.nchild[node]; ++k) tried |= 1u << t.action[t.child[node][k]];
       const int n_un = 4 - __popc(tried);
       if (n_un > 0) {
+        g.ensure();
         int pick = g.below(n_un), act = 0;                                   // random.choice(untried), :274
         for (int k = 0; k < 4; ++k) {
           const int cand = (k == 1) ? 2 : (k == 2) ? 1 : k;
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
       bool rdone = false;
       int steps = 0, fails = 0;
       while (!rdone && steps < a.L) {
+        g.ensure();
         if (s.dest == kNone && current_port(w, s) < 0) { st = SHIPENV_ST_NO_DEST; break; }
         int cat, val;
         if (sample_action(w, s, g, cat, val) != SHIPENV_ST_OK) { st = SHIPENV_ST_SAMPLE_CRASH; break; }

@@ -89,6 +89,50 @@ struct Rng {
     return unit_double(m);
   }
 };
+
+// The same word stream behind a small FIFO in shared memory (8 words per thread, word-interleaved so that the
+// threads of a warp never conflict).  Long sequential consumers (rollouts, MCTS) call ensure() once per
+// environment step: every lane of the warp then refills at ONE code site, in lock-step, instead of each lane
+// running Philox at whichever of the many next() call sites it happens to cross a block boundary.
+struct RngFifo {
+  const uint32_t* rk;
+  uint32_t* slot;          // this thread's column of the shared [8][blockDim.x] word array
+  uint32_t stride;         // blockDim.x
+  uint32_t c1, c2, c3;
+  uint32_t i;              // next word of the cell to hand out
+  uint32_t filled;         // words generated so far (multiple of 4); words [filled-8, filled) are resident
+
+  __device__ __forceinline__ void seek(const uint32_t* round_keys, uint32_t* column, uint32_t column_stride,
+                                       uint32_t cell1, uint64_t id) {
+    rk = round_keys; slot = column; stride = column_stride;
+    c1 = cell1; c2 = uint32_t(id); c3 = uint32_t(id >> 32);
+    i = 0; filled = 0;
+  }
+  __device__ __forceinline__ void refill() {
+    uint32_t w[4];
+    philox4x32_10(filled >> 2, c1, c2, c3, rk[0], rk[1], w);
+    const uint32_t base = filled & 7u;                 // 0 or 4
+#pragma unroll
+    for (int k = 0; k < 4; ++k) slot[(base + k) * stride] = w[k];
+    filled += 4;
+  }
+  // at least 4 words ahead: the common step (choice, fuel cost, loss draw) then never refills inside
+  __device__ __forceinline__ void ensure() { if (filled - i < 4u) refill(); }
+  __device__ __forceinline__ uint32_t next() {
+    if (i == filled) refill();                         // rare: a step that needs more than the words ahead
+    const uint32_t w = slot[(i & 7u) * stride];
+    ++i;
+    return w;
+  }
+  __device__ __forceinline__ double random() { return unit_double(next()); }
+  __device__ __forceinline__ int below(int n) { return int(__umulhi(next(), uint32_t(n))); }
+  __device__ __forceinline__ int randint(int a, int b) { return a + below(b - a + 1); }
+  __device__ __forceinline__ double beta22() {
+    const uint32_t a = next(), b = next(), c = next();
+    const uint32_t m = max(min(a, b), min(max(a, b), c));
+    return unit_double(m);
+  }
+};
 #endif
 
 }  // namespace shipenv

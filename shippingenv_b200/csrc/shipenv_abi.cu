@@ -465,7 +465,7 @@ int shipenv_rollout(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S,
   RolloutArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, returns,
                 reinterpret_cast<uint4*>(final), steps, status, seed, root_id_base, {}};
   fill_round_keys(a.round_key, seed, kRolloutTweak);
-  const size_t smem = c->world_bytes;
+  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + 8 * 4 * kRolloutThreads;   // world + word FIFO
   const int64_t tiles = (R * int64_t(S) + kRolloutThreads - 1) / kRolloutThreads;
   int grid = 0;
   if (int rc = grid_for(c, rollout_kernel, c->occ_rollout, kRolloutThreads, smem, tiles, &grid)) return rc;
@@ -495,7 +495,7 @@ int shipenv_mcts(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S, in
   MctsArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, c_param, c->d_log_table,
              action, root_visits, child_action, child_visits, child_total, status, seed, root_id_base, {}};
   fill_round_keys(a.round_key, seed, kRolloutTweak);
-  const size_t smem = c->world_bytes;
+  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + 8 * 4 * kMctsThreads;   // world + word FIFO
   int grid = 0;
   if (int rc = grid_for(c, mcts_kernel, c->occ_mcts, kMctsThreads, smem, (R + kMctsThreads - 1) / kMctsThreads, &grid)) return rc;
   mcts_kernel<<<grid, kMctsThreads, smem, stream>>>(a);

@@ -44,7 +44,8 @@ __device__ __forceinline__ int current_port(const WorldView& w, const ShipR& s) 
 }
 
 // reset (:227-243).  P >= 2 is enforced on the host (the reference never terminates for P == 1).
-__device__ __forceinline__ void env_reset(const WorldView& w, ShipR& s, Rng& g) {
+template <class G>
+__device__ __forceinline__ void env_reset(const WorldView& w, ShipR& s, G& g) {
   const int P = w.h->P;
   s.cargo = w.h->cargo0;
   s.fuel = w.h->fuel0;
@@ -57,7 +58,8 @@ __device__ __forceinline__ void env_reset(const WorldView& w, ShipR& s, Rng& g) 
 }
 
 // _move_ship (:273-339); m = 0..3 = N, E, S, W = (0,-1), (-1,0), (0,1), (1,0) (shipping/type.py:13-16).
-__device__ __forceinline__ int do_move(const WorldView& w, ShipR& s, Rng& g, int m, double& reward, bool& done) {
+template <class G>
+__device__ __forceinline__ int do_move(const WorldView& w, ShipR& s, G& g, int m, double& reward, bool& done) {
   if (s.dest == kNone) return SHIPENV_ST_NO_DEST;                               // :276
   const int dx = (m == 3) - (m == 1), dy = (m == 2) - (m == 0);
   const int sx = s.x, sy = s.y, nx = sx + dx, ny = sy + dy;
@@ -109,7 +111,8 @@ __device__ __forceinline__ int do_move(const WorldView& w, ShipR& s, Rng& g, int
 }
 
 // step's dispatch (:359-376) with _select_port (:265-271), _take_cargo (:341-348), _take_fuel (:350-357).
-__device__ __forceinline__ int do_action(const WorldView& w, ShipR& s, Rng& g, int cat, int val,
+template <class G>
+__device__ __forceinline__ int do_action(const WorldView& w, ShipR& s, G& g, int cat, int val,
                                          double& reward, bool& done) {
   if (w.h->P == 0) return SHIPENV_ST_NO_PORTS;                                   // :360
   done = false;
@@ -156,7 +159,8 @@ __device__ __forceinline__ int encode_action(int cat, int val, int P) {
 }
 
 // sample_action (:245-263).  Returns 0 or SHIPENV_ST_SAMPLE_CRASH (the fuel == 0 branch, :163).
-__device__ __forceinline__ int sample_action(const WorldView& w, const ShipR& s, Rng& g, int& cat, int& val) {
+template <class G>
+__device__ __forceinline__ int sample_action(const WorldView& w, const ShipR& s, G& g, int& cat, int& val) {
   const int cur = current_port(w, s);
   const int P = w.h->P;
   if (s.dest == kNone && cur >= 0) {                                             // :247-254
@@ -174,7 +178,8 @@ __device__ __forceinline__ int sample_action(const WorldView& w, const ShipR& s,
 }
 
 // `a = sample_action(); try: step(a) except: continue` (agents/mcts.py:228-236), bounded by kMaxTries.
-__device__ __forceinline__ int policy_step(const WorldView& w, ShipR& s, Rng& g, double& reward, bool& done, int& taken) {
+template <class G>
+__device__ __forceinline__ int policy_step(const WorldView& w, ShipR& s, G& g, double& reward, bool& done, int& taken) {
   if (w.h->P == 0) return SHIPENV_ST_NO_PORTS;
   if (s.dest == kNone && current_port(w, s) < 0) return SHIPENV_ST_NO_DEST;  // the reference spins forever here
   int last = SHIPENV_ST_OFF_MAP;
