@@ -350,6 +350,17 @@ def run_ours(args):
                                            "what": "fused preprocess_state rows, f32 [n, 26], TMA bulk stores"}
         ms = timed(lambda: g0.valid_action_bits(), 50)
         extras["valid_action_mask"] = {"envs_per_s": n / (ms * 1e-3), "ms_per_launch": ms}
+        # BASELINE configs[1]: 4,096 envs -- launch-bound; eager launches vs one CUDA-graph replay of 256 steps
+        small = BatchedEnvironment(4096, passable=world(), seed=SEED, device=dev, max_steps=MAX_STEPS)
+        small.reset()
+        sact = torch.randint(0, 4, (256, 4096), generator=gen, device=dev, dtype=torch.int16)
+        ms = timed(lambda: [small.step(sact[t]) for t in range(256)], 3)
+        graph = small.capture_steps(sact)
+        msg = timed(lambda: graph.replay(), 10)
+        extras["config_4096_envs"] = {"eager_env_steps_per_s": 4096 * 256 / (ms * 1e-3),
+                                      "cuda_graph_env_steps_per_s": 4096 * 256 / (msg * 1e-3),
+                                      "us_per_step_eager": ms * 1e3 / 256, "us_per_step_graph": msg * 1e3 / 256,
+                                      "what": "BASELINE configs[1]: 4,096 envs on one GPU, random moves, auto-reset"}
         R, S, L = 65536, 50, 100                      # BASELINE configs[3]
         roots = g0.ships[:R].contiguous()
         holder = {}

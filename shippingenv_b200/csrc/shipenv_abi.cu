@@ -65,8 +65,7 @@ struct shipenv_ctx {
   // device blob
   void* d_world = nullptr;
   double* d_log_table = nullptr;        // shipenv_mcts: log(n), n = 0..SHIPENV_MCTS_MAX_SIMS+1
-  uint32_t* d_tile_counter = nullptr;   // ticket counter of step_fast_kernel's tile scheduler
-  uint32_t tile_base = 0;
+  uint32_t* d_tile_counter = nullptr;   // ticket counter of step_fast_kernel's tile scheduler (self-resetting)
   std::vector<unsigned char> h_world;
   uint32_t world_bytes = 0;
   bool dirty = true;
@@ -337,7 +336,6 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
     const int64_t fast_tiles = (n + int64_t(kThreads) * ept - 1) / (int64_t(kThreads) * ept);
     if (int rc = grid_for(c, kernel, *occ, kStepBlock, smem, fast_tiles, &grid)) return rc;
     a.tile_counter = c->d_tile_counter;
-    a.tile_base = c->tile_base;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStepBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -345,12 +343,6 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // with the previous grid's tail
     cfg.attrs = attr; cfg.numAttrs = 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a));
-    // counter tickets this launch consumes: one per tile-or-end-marker a CTA fetches after its first (static) tile
-    {
-      const uint32_t full = uint32_t(n / (int64_t(kThreads) * ept));
-      const uint32_t starters = full < uint32_t(grid) ? full : uint32_t(grid);   // CTAs whose first tile exists
-      c->tile_base += (full - starters) + starters;   // every remaining tile once + one failed fetch per started CTA
-    }
   } else if (a.io.obs) {
     if (!actions) return fail(SHIPENV_E_ARG, "step: this output set needs the `actions` array even with SHIPENV_F_ALL_POLICY");
     const size_t base = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + ((kPipeBytes + 127) & ~size_t(127));

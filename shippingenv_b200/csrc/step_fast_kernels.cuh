@@ -82,9 +82,11 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid >= kThreads) {             // ---- producer warp: lane 0 streams tiles in with TMA ----
     if (tid == kThreads) {
-      // Tiles are handed out by a global ticket counter, so SMs that run ahead simply take more tiles
-      // (no tail imbalance).  The counter is never reset: the host passes the ticket this launch starts at.
-      // tickets 0..grid-1 are the block indices; later ones come from the counter (offset by the grid size)
+      // Tiles are handed out by a global ticket counter, so SMs that run ahead simply take more tiles (no tail
+      // imbalance).  Tickets 0..grid-1 are the block indices; later ones come from the counter, offset by the
+      // grid size.  Every tile load is followed by exactly one fetch, so a launch makes exactly `full_tiles`
+      // fetches: the thread that draws the last one puts the counter back to zero for the next launch (which
+      // cannot fetch before this grid has completed).  No host-side state: the launch is CUDA-graph replayable.
       uint32_t ticket = blockIdx.x;
       for (int it = 0;; ++it) {
         const int st = it % kStages;
@@ -100,7 +102,9 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         tma_load_bulk(stage[st].ships, a.ships + base, kTile * 16u, &full_bar[st]);
         tma_load_bulk(stage[st].clock, a.clock + base, kTile * 4u, &full_bar[st]);
         if (!kPolicy) tma_load_bulk(stage[st].act, a.actions + base, kTile * 2u, &full_bar[st]);
-        ticket = atomicAdd(a.tile_counter, 1u) - a.tile_base + gridDim.x;   // in flight while the slot is awaited
+        const uint32_t drawn = atomicAdd(a.tile_counter, 1u);      // in flight while the slot is awaited
+        if (drawn == uint32_t(full_tiles) - 1u) atomicExch(a.tile_counter, 0u);
+        ticket = drawn + gridDim.x;
       }
     }
     return;

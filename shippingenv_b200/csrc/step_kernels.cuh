@@ -23,8 +23,7 @@ struct StepArgs {
   int obs_width;            // 6 + 4P
   int obs_bufs;             // observation tiles resident in shared memory (1 or 2)
   uint32_t round_key[20];   // Philox round keys of `seed`: (k0 + r*W0, k1 + r*W1), r = 0..9
-  uint32_t* tile_counter;   // step_fast_kernel: global ticket counter (context-owned, never reset)
-  uint32_t tile_base;       // ticket value this launch starts at
+  uint32_t* tile_counter;   // step_fast_kernel: global ticket counter (context-owned, zero between launches)
 };
 
 // Observation row head (utils/preprocessing.py:53-60): x, y, fuel, "cargo" (= fuel, the

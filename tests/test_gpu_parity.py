@@ -388,3 +388,27 @@ def test_cuda_policy_fast_kernel(torch_cuda, default_map, n, max_steps):
     assert n_reset > 0
     if n > 1000:
         assert n_arrive > 0
+
+
+def test_cuda_graph_replay_of_steps(torch_cuda, default_map):
+    """BASELINE configs[1] (4,096 envs): T steps captured in a CUDA graph == the same T steps launched one by one,
+    and a second replay keeps going exactly like T more eager steps (no host-side state in the launches)."""
+    torch = torch_cuda
+    from shippingenv_b200 import BatchedEnvironment
+    n, T, seed = 4096, 24, 31
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.randint(0, 4, (T, n), generator=gen, device="cuda", dtype=torch.int16)
+    eager = BatchedEnvironment(n, passable=default_map["passable"], seed=seed, device="cuda:0", max_steps=30)
+    graphed = BatchedEnvironment(n, passable=default_map["passable"], seed=seed, device="cuda:0", max_steps=30)
+    eager.reset(); graphed.reset()
+    graphed.step(acts[0]); eager.step(acts[0])                # warm the launch path outside the capture
+    state0 = graphed.ships.clone(), graphed.clock.clone()
+    g = graphed.capture_steps(acts)
+    graphed.ships.copy_(state0[0]); graphed.clock.copy_(state0[1])   # the capture itself does not run the steps
+    for rep in range(2):
+        g.replay()
+        for t in range(T):
+            eager.step(acts[t])
+        torch.cuda.synchronize()
+        assert torch.equal(eager.ships, graphed.ships) and torch.equal(eager.clock, graphed.clock), rep
+        assert torch.equal(eager.reward, graphed.reward) and torch.equal(eager.reset_bits, graphed.reset_bits)
