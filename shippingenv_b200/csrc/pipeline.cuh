@@ -82,6 +82,11 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ int lds_s16(uint32_t saddr) {
   short v;
   asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(saddr));

@@ -72,7 +72,7 @@ struct shipenv_ctx {
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_step_fast, occ_step_fast_policy, occ_fast_o, occ_fast_po, occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid, occ_mcts;
+  Occ occ_fast[8], occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid, occ_mcts;
 };
 
 namespace {
@@ -318,21 +318,28 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   const int64_t tiles = (n + kThreads - 1) / kThreads;
   const bool lean = !a.io.reward_f64 && !a.io.status && !a.io.taken && !a.io.ep_return;
   int grid = 0;
-  const bool fast_ok = lean && a.io.reward_f32 && a.io.done_bits && a.io.reset_bits && a.io.error_bits && word0 == 0 &&
+  const bool fast_ok = a.io.done_bits && a.io.reset_bits && a.io.error_bits && (a.io.reward_f32 || !lean) && word0 == 0 &&
                        c->P >= 2 && !c->no_fast_kernel;
   if (a.io.obs && (reinterpret_cast<uintptr_t>(a.io.obs) & 15u)) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
   if (fast_ok) {
-    // throughput kernels: step_fast_kernel<policy, obs>
+    // throughput kernels: step_fast_kernel<policy, obs, envs per thread, lean>
     constexpr int kEpt = SHIPENV_FAST_EPT;
     const int ept = a.io.obs ? 1 : kEpt;
     size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + (a.io.obs ? fast_smem_bytes<1>() : fast_smem_bytes<kEpt>());
     if (a.io.obs) smem += 2 * size_t(kThreads) * a.obs_width * 4;
     void (*kernel)(const StepArgs) = nullptr;
-    shipenv_ctx::Occ* occ = nullptr;
-    if (a.io.obs) { kernel = all_policy ? step_fast_kernel<true, true, 1> : step_fast_kernel<false, true, 1>;
-                    occ = all_policy ? &c->occ_fast_po : &c->occ_fast_o; }
-    else { kernel = all_policy ? step_fast_kernel<true, false, kEpt> : step_fast_kernel<false, false, kEpt>;
-           occ = all_policy ? &c->occ_step_fast_policy : &c->occ_step_fast; }
+    const int variant = (all_policy ? 4 : 0) | (a.io.obs ? 2 : 0) | (lean ? 1 : 0);
+    switch (variant) {
+      case 0: kernel = step_fast_kernel<false, false, kEpt, false>; break;
+      case 1: kernel = step_fast_kernel<false, false, kEpt, true>; break;
+      case 2: kernel = step_fast_kernel<false, true, 1, false>; break;
+      case 3: kernel = step_fast_kernel<false, true, 1, true>; break;
+      case 4: kernel = step_fast_kernel<true, false, kEpt, false>; break;
+      case 5: kernel = step_fast_kernel<true, false, kEpt, true>; break;
+      case 6: kernel = step_fast_kernel<true, true, 1, false>; break;
+      default: kernel = step_fast_kernel<true, true, 1, true>; break;
+    }
+    shipenv_ctx::Occ* occ = &c->occ_fast[variant];
     const int64_t fast_tiles = (n + int64_t(kThreads) * ept - 1) / (int64_t(kThreads) * ept);
     if (int rc = grid_for(c, kernel, *occ, kStepBlock, smem, fast_tiles, &grid)) return rc;
     a.tile_counter = c->d_tile_counter;

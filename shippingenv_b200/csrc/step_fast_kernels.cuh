@@ -40,7 +40,9 @@ constexpr size_t fast_smem_bytes() {   // ring slots + full/empty mbarriers + ti
 // kObs: fused observation rows (utils/preprocessing.py:25-62): lanes that need the general path are resolved on the
 // spot (their row must be final before the tile's TMA bulk store), heads go to a shared [256, 6+4P] tile whose
 // constant port tail is written once, one bulk store per tile, two tiles in flight.
-template <bool kPolicy, bool kObs, int kEpt>
+// kLean: only reward_f32 and the masks exist; otherwise status / taken / reward_f64 / episode statistics are
+// written too (each still nullable), for the straight-line lanes here and by the general path for the others.
+template <bool kPolicy, bool kObs, int kEpt, bool kLean>
 __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
@@ -236,7 +238,18 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
           st_stream_u4(a.ships + i, out);
           a.clock[i] = c_out;
         }
-        if (!general) a.io.reward_f32[i] = ok ? r : 0.f;
+        if (!general && (kLean || a.io.reward_f32)) a.io.reward_f32[i] = ok ? r : 0.f;
+        if (!kLean) {
+          if (!general) {              // accepted straight-line move, or an explicit off-map move
+            const double r64 = ok ? lds_f64(wb + uint32_t(offsetof(WorldHdr, move_reward)) +
+                                            ((uint32_t(no_fuel) << 2) | (uint32_t(!water) << 1) | uint32_t(closer)) * 8u)
+                                  : 0.0;
+            if (a.io.reward_f64) a.io.reward_f64[i] = r64;
+            if (a.io.status) a.io.status[i] = uint8_t(ok ? SHIPENV_ST_OK : SHIPENV_ST_OFF_MAP);
+            if (a.io.taken) a.io.taken[i] = int16_t(kPolicy ? m : act);
+            if (ok) track_episode(a.io, i, r64, do_reset, c);
+          }
+        }
         if (kObs) fin = ok ? out : rec;
       }
       const uint32_t gen_w = __ballot_sync(0xFFFFFFFFu, general);
