@@ -29,7 +29,7 @@ constexpr size_t fast_smem_bytes() {   // ring slots + full/empty mbarriers + ti
   return sizeof(FastStage<kEpt>) * kStages + 2 * 8 * kStages + 4 * kStages + size_t(kDeferCap) * kEpt * 4 * (kThreads / 32);
 }
 #ifndef SHIPENV_FAST_EPT
-#define SHIPENV_FAST_EPT 1
+#define SHIPENV_FAST_EPT 2
 #endif
 
 #ifndef SHIPENV_FAST_MIN_BLOCKS
@@ -203,15 +203,17 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const double cost = __dadd_rn(1.0, __dadd_rn(-0.1, __dmul_rn(0.1 - (-0.1), unit_double(w_cost))));   // :103-104
       const bool no_fuel = fuel < cost;                                                   // :288
       const uint32_t cell = in_map ? nx * wpr + (ny >> 5) : 0u;
-      const bool water = (lds_u32(bits_b + cell * 4u) >> (ny & 31u)) & 1u;                // :293
+      const uint32_t wbit = (lds_u32(bits_b + cell * 4u) >> (ny & 31u)) & 1u;             // :293, 1 = not ground
+      const bool water = wbit != 0u;
       const uint32_t pd = lds_u32(wb + uint32_t(offsetof(WorldHdr, port)) + (dest & 31u) * 4u);
-      const uint32_t tx = pd & 255u, ty = (pd >> 8) & 255u;
+      const int tx = int(pd & 255u), ty = int((pd >> 8) & 255u);
       // closer <=> d_prev - d_new > 0 <=> (x - tx) * dx + (y - ty) * dy < 0 for a unit move   (:309-312)
-      const bool closer = (int(x) - int(tx)) * dx + (int(y) - int(ty)) * dy < 0;
-      const uint32_t px = water ? nx : x, py = water ? ny : y;
+      const uint32_t closer_bit = uint32_t((int(x) - tx) * dx + (int(y) - ty) * dy) >> 31;
+      // positions stay packed as x | y << 8 (the low half of the record's first word)
+      const uint32_t pos1 = water ? (nx | (ny << 8)) : (rec.x & 0xFFFFu);
       // loss_thr[cap] = 0xFFFFFFFF: cargo >= capacity always draws; negative cargo goes the general way
       const bool trigger = w_loss <= lds_u32(wb + uint32_t(offsetof(WorldHdr, loss_thr)) + min(uint32_t(rec.y), cap) * 4u);  // :318-320
-      const bool arrive = px == tx && py == ty;                                           // :325
+      const bool arrive = pos1 == (pd & 0xFFFFu);                                         // :325
       const uint32_t c1 = c + 1u;
       const bool do_reset = auto_reset && (no_fuel || (c1 & 0xFFFFu) >= trunc_at);
       const uint32_t ro = __umulhi(wd[2], P), rd = __umulhi(wd[3], P);                    // :232-233
@@ -220,10 +222,11 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
                                    : (!is_move || (in_map && (trigger || arrive || (do_reset && ro == rd))));
       const bool ok = is_move && in_map && !general;
       const bool off_map = !kPolicy && is_move && !in_map;
+      const uint32_t ridx = (no_fuel ? 4u : 0u) | ((wbit ^ 1u) << 1) | closer_bit;        // index of move_reward[]
       {
         const double fuel1 = water ? __dsub_rn(fuel, cost) : fuel;                        // :298
         uint4 out;
-        out.x = px | (py << 8) | (rec.x & 0xFFFF0000u);
+        out.x = (rec.x & 0xFFFF0000u) | pos1;
         out.y = rec.y;
         out.z = uint32_t(__double2loint(fuel1)); out.w = uint32_t(__double2hiint(fuel1));
         uint32_t c_out = c1;
@@ -232,8 +235,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
           out.y = reset_rec_y; out.z = reset_rec_z; out.w = reset_rec_w;
           c_out = ((c >> 16) + 1u) << 16;
         }
-        const float r = lds_f32(wb + uint32_t(offsetof(WorldHdr, move_reward_f32)) +
-                                ((uint32_t(no_fuel) << 2) | (uint32_t(!water) << 1) | uint32_t(closer)) * 4u);
+        const float r = lds_f32(wb + uint32_t(offsetof(WorldHdr, move_reward_f32)) + ridx * 4u);
         if (ok) {
           st_stream_u4(a.ships + i, out);
           a.clock[i] = c_out;
@@ -241,9 +243,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         if (!general && (kLean || a.io.reward_f32)) a.io.reward_f32[i] = ok ? r : 0.f;
         if (!kLean) {
           if (!general) {              // accepted straight-line move, or an explicit off-map move
-            const double r64 = ok ? lds_f64(wb + uint32_t(offsetof(WorldHdr, move_reward)) +
-                                            ((uint32_t(no_fuel) << 2) | (uint32_t(!water) << 1) | uint32_t(closer)) * 8u)
-                                  : 0.0;
+            const double r64 = ok ? lds_f64(wb + uint32_t(offsetof(WorldHdr, move_reward)) + ridx * 8u) : 0.0;
             if (a.io.reward_f64) a.io.reward_f64[i] = r64;
             if (a.io.status) a.io.status[i] = uint8_t(ok ? SHIPENV_ST_OK : SHIPENV_ST_OFF_MAP);
             if (a.io.taken) a.io.taken[i] = int16_t(kPolicy ? m : act);
