@@ -271,12 +271,11 @@ def run_ours(args):
 
     def run_steps(count):
         for t in range(count):
-            g = t % G
-            with torch.cuda.stream(gstreams[g]):
-                envs[g].step(pool[t % ACTION_POOL])
+            envs[t % G].step(pool[t % ACTION_POOL])       # env g launches on its own stream (use_stream below)
 
-    for st in gstreams:
+    for g, st in enumerate(gstreams):
         st.wait_stream(torch.cuda.current_stream(dev))
+        envs[g].use_stream(st)
     run_steps(W)
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -287,7 +286,9 @@ def run_ours(args):
         e0.record()
         for st in gstreams:
             st.wait_event(e0)
+        t_host = time.perf_counter()
         run_steps(K)
+        host_us = (time.perf_counter() - t_host) / K * 1e6     # host cost of one launch (must stay below the GPU time)
         for g, st in enumerate(gstreams):
             g_end[g].record(st)
         barrier()
@@ -296,6 +297,8 @@ def run_ours(args):
     err = int(sum(int(e.error_bits.ne(0).sum().item()) for e in envs))
 
     # ---- the same K launches on ONE stream (strictly back to back), reported separately ----
+    for e in envs:
+        e.use_stream(None)
     barrier()
     e0.record()
     for t in range(K):
@@ -437,7 +440,7 @@ def run_ours(args):
                     "what": "shipenv_step via BatchedEnvironment.step: int16 actions from pinned host memory, f32 reward "
                             "+ done/reset masks to pinned host memory; one stream per env group so that copies "
                             "overlap kernels"},
-            "gpu_launches": launches, "clocks": clocks.summary(), "cpus_pinned_to_gpu_numa_node": numa,
+            "gpu_launches": launches, "host_us_per_launch": host_us, "clocks": clocks.summary(), "cpus_pinned_to_gpu_numa_node": numa,
             "rejected_actions_last_step": err, "reward_checksum": checksum,
         }
         if extras:

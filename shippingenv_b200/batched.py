@@ -100,6 +100,7 @@ class BatchedEnvironment:
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
             self.stats = new_stats(dev)
         self._policy = None
+        self.stream, self._stream_handle = None, None
         self._step_cache, self._io_keepalive = {}, []
         self._lib_step = nat.lib().shipenv_step
         self._ctx_handle = self.ctx._h
@@ -119,8 +120,16 @@ class BatchedEnvironment:
     @property
     def fuel(self): return self.ships.view(torch.float64)[:, 1]
 
+    def use_stream(self, stream):
+        """Launch everything of this environment on ``stream`` (a torch.cuda.Stream) instead of the current stream;
+        ``None`` goes back to the current stream.  Independent env groups on separate streams overlap their launch
+        boundaries; the caller orders them against producers / consumers of their tensors (wait_stream / events)."""
+        self.stream = stream
+        self._stream_handle = None if stream is None else stream.cuda_stream
+
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        h = self._stream_handle
+        return h if h is not None else torch.cuda.current_stream(self.device).cuda_stream
 
     def _buf(self, name, shape, dtype):
         t = getattr(self, name)
@@ -153,7 +162,7 @@ class BatchedEnvironment:
         flags = (nat.F_AUTO_RESET if self.auto_reset else 0) | (nat.F_ALL_POLICY if actions is self._policy else 0)
         rc = self._lib_step(self._ctx_handle, self._ships_ptr, self._clock_ptr, actions.data_ptr(), io_ref, self.seed,
                             self.env_id_base, self.n, self.max_steps, flags,
-                            word0, torch.cuda.current_stream(self.device).cuda_stream)
+                            word0, self._stream())
         if rc:
             nat.check(rc)
         return res
