@@ -163,6 +163,17 @@ int shipenv_sample_action(shipenv_ctx *ctx, const shipenv_ship *ships, const uin
                           int16_t *actions_out, uint8_t *words_used, uint8_t *status,
                           uint64_t seed, uint64_t env_id_base, int64_t n, uint32_t word0, void *stream);
 
+/* shipenv_step followed by the shipenv_sample_action call the reference's loops make next
+ * (`a = env.sample_action(); env.step(a)`: agents/mcts.py:222-230, agents/sarsa.py:211-220), in one launch:
+ * next_action[i] / next_words[i] / next_status[i] (the last two nullable) are what shipenv_sample_action would
+ * return for env i after this step -- drawn from word 0 of the new cell when the step was accepted, from `word0`
+ * of the unchanged cell when it was rejected.  io->obs must be NULL.  General path, one env per thread: meant
+ * for the N = 1 facade (sample_action() after step() then costs no launch), correct for any n. */
+int shipenv_step_sample(shipenv_ctx *ctx, shipenv_ship *ships, uint32_t *clock, const int16_t *actions,
+                        const shipenv_step_io *io, int16_t *next_action, uint8_t *next_words,
+                        uint8_t *next_status, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
+                        uint32_t flags, uint32_t word0, void *stream);
+
 /* _build_state + preprocess_state (shipping/environment.py:202-225, utils/preprocessing.py:25-62)
  * as float32 rows [n, 6+4P] (the dtype the DQN feeds its network, agents/dqn.py:198). */
 int shipenv_observe(shipenv_ctx *ctx, const shipenv_ship *ships, float *obs, int64_t n, void *stream);
@@ -214,6 +225,16 @@ void shipenv_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
 void shipenv_port_stock(uint64_t seed, uint32_t port_index, uint8_t *fuel, uint8_t *cargo);
 /* kernels launched by this process so far (bench.py's gpu_launches) */
 uint64_t shipenv_launch_count(void);
+
+/* ---- host-resident single ship: what the N = 1 drop-in Environment uses ------------------- */
+/* The reference's Environment keeps its ship in Python attributes (shipping/environment.py:36-42).  The facade
+ * mirrors them in one page-locked host block and lets the N = 1 kernels read and write that block in place over
+ * PCIe instead of staging it through device memory.  `host_ptr` must be page-locked (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory); *device_ptr is the address the entry points above accept for it. */
+int shipenv_host_device_pointer(void *host_ptr, void **device_ptr);
+/* Blocks the caller until the work enqueued on `stream` so far has completed (the facade's step() returns
+ * Python values, like shipping/environment.py:376, so it has to wait).  Nothing else in this ABI synchronises. */
+int shipenv_stream_synchronize(shipenv_ctx *ctx, void *stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,9 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_void_p]),
     "shipenv_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(StepIO), C.c_uint64,
                                C.c_uint64, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "shipenv_step_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(StepIO), C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_uint32,
+                                      C.c_uint32, C.c_void_p]),
     "shipenv_sample_action": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]),
     "shipenv_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -79,6 +82,8 @@ _SIGNATURES = {
     "shipenv_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "shipenv_port_stock": (None, [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]),
     "shipenv_launch_count": (C.c_uint64, []),
+    "shipenv_host_device_pointer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "shipenv_stream_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -123,6 +128,13 @@ def port_stock(seed, port_index):
 
 def launch_count():
     return int(lib().shipenv_launch_count())
+
+
+def host_device_pointer(host_ptr):
+    """Device-visible address of a page-locked host allocation (e.g. ``tensor.pin_memory().data_ptr()``)."""
+    out = C.c_void_p()
+    check(lib().shipenv_host_device_pointer(C.c_void_p(host_ptr), C.byref(out)))
+    return int(out.value)
 
 
 class Context:
@@ -193,6 +205,14 @@ class Context:
     def step(self, ships, clock, actions, io, seed, env_id_base, n, max_steps, flags, word0, stream):
         check(lib().shipenv_step(self._h, ships, clock, actions, C.byref(io), seed, env_id_base, n, max_steps,
                                  flags, word0, stream))
+
+    def step_sample(self, ships, clock, actions, io, next_action, next_words, next_status, seed, env_id_base, n,
+                    max_steps, flags, word0, stream):
+        check(lib().shipenv_step_sample(self._h, ships, clock, actions, C.byref(io), next_action, next_words,
+                                        next_status, seed, env_id_base, n, max_steps, flags, word0, stream))
+
+    def synchronize(self, stream):
+        check(lib().shipenv_stream_synchronize(self._h, stream))
 
     def sample_action(self, ships, clock, actions, words_used, status, seed, env_id_base, n, word0, stream):
         check(lib().shipenv_sample_action(self._h, ships, clock, actions, words_used, status, seed, env_id_base,

@@ -98,6 +98,50 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// step followed by the next sample_action: the shape of the reference's loops
+// (`a = env.sample_action(); env.step(a)`, agents/mcts.py:222-230, agents/sarsa.py:211-220).  One env per
+// thread through the general path, then the draw the next sample_action() call would make: from word 0 of the
+// new cell after an accepted step, from `word0` of the same cell after a rejected one (nothing was consumed).
+// The N = 1 facade uses it so that sample_action() after step() needs no launch of its own.
+// ------------------------------------------------------------------------------------------
+struct StepSampleArgs {
+  StepArgs s;
+  int16_t* next_action; uint8_t* next_words; uint8_t* next_status;
+};
+
+__global__ void __launch_bounds__(kThreads) step_sample_kernel(const __grid_constant__ StepSampleArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t world_bar;
+  stage_world(smem, a.s.world, a.s.world_bytes, &world_bar);
+  const WorldView w(smem);
+  const int n = int(a.s.n);
+  const int n_tiles = (n + kThreads - 1) / kThreads;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int i = tile * kThreads + int(threadIdx.x);
+    const bool live = i < n;
+    const uint32_t flags = live ? step_general_inline(a.s, smem, i) : 0u;
+    const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, flags & kFlagDone);
+    const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, flags & kFlagReset);
+    const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, flags & kFlagError);
+    if ((threadIdx.x & 31) == 0 && live) {
+      if (a.s.io.done_bits) a.s.io.done_bits[i >> 5] = done_w;
+      if (a.s.io.reset_bits) a.s.io.reset_bits[i >> 5] = reset_w;
+      if (a.s.io.error_bits) a.s.io.error_bits[i >> 5] = err_w;
+    }
+    if (!live) continue;
+    const ShipR s = unpack(a.s.ships[i]);
+    const uint32_t word0 = (flags & kFlagError) ? a.s.word0 : 0u;
+    Rng g;
+    g.seek(a.s.round_key, a.s.clock[i], a.s.env_id_base + uint64_t(uint32_t(i)), word0);
+    int cat = kCatJunk, val = 0;
+    const int st = w.h->P == 0 ? SHIPENV_ST_NO_PORTS : sample_action(w, s, g, cat, val);
+    a.next_action[i] = st == SHIPENV_ST_OK ? int16_t(encode_action(cat, val, w.h->P)) : int16_t(-2);
+    if (a.next_words) a.next_words[i] = uint8_t(g.i - word0);
+    if (a.next_status) a.next_status[i] = uint8_t(st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // DQN valid-action mask (agents/dqn.py:125-175), one env per thread, ceil(A/32) words per env
 // ------------------------------------------------------------------------------------------
 struct ValidArgs {

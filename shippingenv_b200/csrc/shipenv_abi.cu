@@ -72,7 +72,7 @@ struct shipenv_ctx {
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_fast[8], occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_rollout, occ_valid, occ_mcts;
+  Occ occ_fast[8], occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_step_sample, occ_rollout, occ_valid, occ_mcts;
 };
 
 namespace {
@@ -189,6 +189,20 @@ void shipenv_port_stock(uint64_t seed, uint32_t port_index, uint8_t* fuel, uint8
   // random.randint(5, 20) twice: fuel then cargo (shipping/environment.py:63-64)
   *fuel = uint8_t(5 + ((uint64_t(w[0]) * 16u) >> 32));
   *cargo = uint8_t(5 + ((uint64_t(w[1]) * 16u) >> 32));
+}
+
+int shipenv_host_device_pointer(void* host_ptr, void** device_ptr) {
+  if (!host_ptr || !device_ptr) return fail(SHIPENV_E_ARG, "null pointer");
+  *device_ptr = nullptr;
+  CUDA_TRY(cudaHostGetDevicePointer(device_ptr, host_ptr, 0));
+  return 0;
+}
+
+int shipenv_stream_synchronize(shipenv_ctx* c, void* stream) {
+  if (int rc = check_ctx(c)) return rc;
+  DeviceGuard guard(c->device);
+  CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return 0;
 }
 
 int shipenv_ctx_create(int device, shipenv_ctx** out) {
@@ -374,6 +388,40 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
       step_kernel<false, false><<<grid, kStepBlock, smem, stream>>>(a);
     }
   }
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int shipenv_step_sample(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* actions,
+                        const shipenv_step_io* io, int16_t* next_action, uint8_t* next_words, uint8_t* next_status,
+                        uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps, uint32_t flags, uint32_t word0,
+                        void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  const bool all_policy = flags & SHIPENV_F_ALL_POLICY;
+  if (n < 0 || (n > 0 && (!ships || !clock || !next_action || (!actions && !all_policy))))
+    return fail(SHIPENV_E_ARG, "step_sample: null buffer or negative n");
+  if (max_steps < 0 || max_steps > 65535) return fail(SHIPENV_E_ARG, "max_steps %d outside 0..65535", max_steps);
+  if (io && io->obs) return fail(SHIPENV_E_ARG, "step_sample: observation rows are not produced here, use shipenv_step");
+  if (n == 0) return 0;
+  if (n >= (int64_t(1) << 31)) return fail(SHIPENV_E_ARG, "step_sample: at most 2^31-1 envs per launch");
+  if (reinterpret_cast<uintptr_t>(ships) & 15u) return fail(SHIPENV_E_ARG, "step_sample: ships must be 16-byte aligned");
+  if ((flags & SHIPENV_F_AUTO_RESET) && c->P < 2) return fail(SHIPENV_E_STATE, "auto-reset needs at least 2 ports");
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  StepSampleArgs a{};
+  a.s.world = c->d_world; a.s.world_bytes = c->world_bytes;
+  a.s.ships = reinterpret_cast<uint4*>(ships); a.s.clock = clock; a.s.actions = actions;
+  if (io) a.s.io = *io;
+  a.s.seed = seed; a.s.env_id_base = env_id_base; a.s.n = n; a.s.max_steps = max_steps; a.s.flags = flags; a.s.word0 = word0;
+  a.s.obs_width = 6 + 4 * c->P;
+  fill_round_keys(a.s.round_key, seed, 0u);
+  a.next_action = next_action; a.next_words = next_words; a.next_status = next_status;
+  const size_t smem = c->world_bytes;
+  int grid = 0;
+  if (int rc = grid_for(c, step_sample_kernel, c->occ_step_sample, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
+  step_sample_kernel<<<grid, kThreads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   ++g_launches;
   return 0;

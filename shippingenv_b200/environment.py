@@ -5,8 +5,9 @@ attributes the agents read and write and turns status codes back into the refere
 
 Contract: the attributes are the source of truth.  Agents assign them wholesale
 (agents/mcts.py:199-208), so before every launch the ship record is packed from the attributes
-and after it they are refreshed from the device.  The world (map + port table) is re-uploaded
-only when it changed.
+into a page-locked host block, the kernel reads and writes that block in place (zero-copy over
+PCIe: one launch + one stream synchronisation per call), and the attributes are refreshed from it.
+The world (map + port table) is re-uploaded only when it changed.
 
 Differences from the reference, all documented in DESIGN.md: draws come from the Philox word
 stream (seeded from ``random`` at construction unless ``seed`` is given) instead of MT19937;
@@ -15,6 +16,7 @@ looping forever; ``sample_action`` with ``fuel == 0`` at a port raises ``TypeErr
 reference does, but never consumes a draw.
 """
 import random as _pyrandom
+import struct
 
 import numpy as np
 import torch
@@ -36,7 +38,12 @@ _ERRORS = {
 }
 
 # byte offsets inside the per-instance 128-byte device / pinned-host block
-_SHIP, _REWARD, _CLOCK, _ACTION, _DONE, _RESET, _ERR, _STATUS, _TAKEN, _WORDS, _BLOCK = 0, 16, 32, 48, 64, 68, 72, 76, 78, 80, 128
+_SHIP, _REWARD, _CLOCK, _ACTION, _DONE, _RESET, _ERR, _STATUS, _TAKEN, _WORDS, _NEXT, _BLOCK = 0, 16, 32, 48, 64, 68, 72, 76, 78, 80, 84, 128
+
+_SHIP_FMT = struct.Struct("<BBBBid")            # shipenv_ship: x, y, origin, dest, cargo, fuel
+_U32, _I16, _F64 = struct.Struct("<I"), struct.Struct("<h"), struct.Struct("<d")
+_NEXT_FMT = struct.Struct("<hBB")                # step_sample: next action, words it used, its status
+_FLAGS_FMT = struct.Struct("<IIIBxhB")           # done, reset, error words, status, taken, words used
 
 _contexts = {}   # device index -> (Context, world signature currently uploaded)
 
@@ -70,9 +77,17 @@ class Environment:
         self._env_id = int(env_id)
         self._clock = 0          # episode << 16 | step: selects the Philox cell of the next step
         self._word = 0           # words of that cell already consumed by sample_action()
-        self._dev = torch.zeros(_BLOCK, dtype=torch.uint8, device=self._device)
+        self._spec = None        # (record, clock, word, world) the last step's look-ahead sample_action was drawn for
+        self._world_sig = None
+        # One page-locked host block per instance; the N = 1 kernels read and write it in place through its
+        # device-visible address (no staging copies: a step is one launch and one stream synchronisation).
         self._host = torch.zeros(_BLOCK, dtype=torch.uint8).pin_memory()
         self._hnp = self._host.numpy()
+        self._buf = memoryview(self._hnp)
+        self._base = nat.host_device_pointer(self._host.data_ptr())
+        self._io = nat.StepIO()
+        self._io.reward_f64, self._io.status = self._ptr(_REWARD), self._ptr(_STATUS)
+        self._io.done_bits, self._io.reset_bits, self._io.error_bits = self._ptr(_DONE), self._ptr(_RESET), self._ptr(_ERR)
         self._passable_key = None
         self._passable = None
 
@@ -105,9 +120,10 @@ class Environment:
                 raise ValueError("np_game does not cover size_game (non-square maps are not supported)")
             self._passable = np.ascontiguousarray(g[:self.size_game[0], :self.size_game[1]] != Entity.GROUND,
                                                   dtype=np.uint8)
+            self._passable_bytes = self._passable.tobytes()
             self._passable_key = key
         ports = [(int(p[0]), int(p[1])) for p in self.port_positions]
-        sig = (self._passable.tobytes(), tuple(ports), tuple(map(int, self.port_fuel)),
+        sig = (self._passable_bytes, tuple(ports), tuple(map(int, self.port_fuel)),
                tuple(map(int, self.port_cargo)))
         slot = _context(self._device.index)
         if slot[1] != sig:
@@ -116,28 +132,27 @@ class Environment:
             slot[0].set_map(self._passable)
             slot[0].set_ports(ports, list(map(int, self.port_fuel)), list(map(int, self.port_cargo)))
             slot[1] = sig
+        self._world_sig = slot[1]
         return slot[0]
 
     def _pack(self, action=0):
-        h = self._hnp
         pos = self.ship_position if len(self.ship_position) == 2 else (0, 0)
-        h[0], h[1] = int(pos[0]) & 255, int(pos[1]) & 255
-        h[2] = nat.NONE_PORT if self.origin_port_index is None else int(self.origin_port_index)
-        h[3] = nat.NONE_PORT if self.destination_port_index is None else int(self.destination_port_index)
-        h[4:8].view(np.int32)[0] = int(self.cargo)
-        h[8:16].view(np.float64)[0] = float(self.fuel)
-        h[_CLOCK:_CLOCK + 4].view(np.uint32)[0] = self._clock
-        h[_ACTION:_ACTION + 2].view(np.int16)[0] = action
-        self._dev[:_DONE].copy_(self._host[:_DONE], non_blocking=True)
+        origin, dest = self.origin_port_index, self.destination_port_index
+        _SHIP_FMT.pack_into(self._buf, _SHIP, int(pos[0]) & 255, int(pos[1]) & 255,
+                            nat.NONE_PORT if origin is None else int(origin),
+                            nat.NONE_PORT if dest is None else int(dest), int(self.cargo), float(self.fuel))
+        _U32.pack_into(self._buf, _CLOCK, self._clock)
+        _I16.pack_into(self._buf, _ACTION, action)
+
+    def _wait(self, ctx):
+        """Returns once the launch has completed; the kernel's stores to the host block are then visible."""
+        ctx.synchronize(self._stream())
 
     def _unpack(self):
-        self._host.copy_(self._dev, non_blocking=False)
-        h = self._hnp
-        return (int(h[0]), int(h[1]), int(h[2]), int(h[3]), int(h[4:8].view(np.int32)[0]),
-                float(h[8:16].view(np.float64)[0]))
+        return _SHIP_FMT.unpack_from(self._buf, _SHIP)
 
     def _ptr(self, off):
-        return self._dev.data_ptr() + off
+        return self._base + off
 
     def _stream(self):
         return torch.cuda.current_stream(self._device).cuda_stream
@@ -177,9 +192,11 @@ class Environment:
         self.np_game[(self.np_game == Entity.BOAT) | (self.np_game == Entity.TRAVEL)] = Entity.WATER
         self._pack()
         ctx.reset(self._ptr(_SHIP), self._ptr(_CLOCK), self._seed, self._env_id, 1, None, self._stream())
+        self._wait(ctx)
         x, y, origin, dest, cargo, fuel = self._unpack()
-        self._clock = int(self._hnp[_CLOCK:_CLOCK + 4].view(np.uint32)[0])
+        self._clock = _U32.unpack_from(self._buf, _CLOCK)[0]
         self._word = 0
+        self._spec = None
         self._adopt(x, y, origin, dest, cargo, fuel, keep_int_fuel=True)
         current_port = self.port_positions[origin]
         self.np_game[current_port[0], current_port[1]] = Entity.BOAT
@@ -189,16 +206,20 @@ class Environment:
     def sample_action(self):
         ctx = self._sync_world()
         self._pack()
-        ctx.sample_action(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_TAKEN), self._ptr(_WORDS),
-                          self._ptr(_STATUS), self._seed, self._env_id, 1, self._word, self._stream())
-        self._host.copy_(self._dev, non_blocking=False)
-        h = self._hnp
-        status = int(h[_STATUS])
+        spec, self._spec = self._spec, None
+        if spec is not None and spec[0] == self._buf[_SHIP:_SHIP + 16] and spec[1:] == (self._clock, self._word, self._world_sig):
+            # the previous step() already drew this call's action for exactly this state (shipenv_step_sample)
+            taken, words, status = _NEXT_FMT.unpack_from(self._buf, _NEXT)
+        else:
+            ctx.sample_action(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_TAKEN), self._ptr(_WORDS),
+                              self._ptr(_STATUS), self._seed, self._env_id, 1, self._word, self._stream())
+            self._wait(ctx)
+            _, _, _, status, taken, words = _FLAGS_FMT.unpack_from(self._buf, _DONE)
         if status != nat.ST_OK:
             exc, msg = _ERRORS[status]
             raise exc(msg)
-        self._word += int(h[_WORDS])
-        return self._decode(int(h[_TAKEN:_TAKEN + 2].view(np.int16)[0]))
+        self._word += words
+        return self._decode(taken)
 
     def _decode(self, a):
         P = len(self.port_positions)
@@ -248,19 +269,20 @@ class Environment:
         old = (int(self.ship_position[0]), int(self.ship_position[1])) if len(self.ship_position) == 2 else None
         fuel_was_int = isinstance(self.fuel, int)
         self._pack(a)
-        io = nat.StepIO()
-        io.reward_f64, io.status = self._ptr(_REWARD), self._ptr(_STATUS)
-        io.done_bits, io.reset_bits, io.error_bits = self._ptr(_DONE), self._ptr(_RESET), self._ptr(_ERR)
-        ctx.step(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_ACTION), io, self._seed, self._env_id, 1, 0, 0,
-                 self._word, self._stream())
+        # the step and, in the same launch, the draw of the sample_action() call that usually follows it
+        ctx.step_sample(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_ACTION), self._io, self._ptr(_NEXT),
+                        self._ptr(_NEXT + 2), self._ptr(_NEXT + 3), self._seed, self._env_id, 1, 0, 0, self._word,
+                        self._stream())
+        self._wait(ctx)
         x, y, origin, dest, cargo, fuel = self._unpack()
-        h = self._hnp
-        status = int(h[_STATUS])
-        if status != nat.ST_OK:       # nothing changed on the device, no draw was consumed
+        done_word, _, _, status, _, _ = _FLAGS_FMT.unpack_from(self._buf, _DONE)
+        if status != nat.ST_OK:       # nothing changed on the device, no draw was consumed: the cell continues
+            self._spec = (bytes(self._buf[_SHIP:_SHIP + 16]), self._clock, self._word, self._world_sig)
             exc, msg = _ERRORS[status]
             raise exc(msg)
-        self._clock = int(h[_CLOCK:_CLOCK + 4].view(np.uint32)[0])
+        self._clock = _U32.unpack_from(self._buf, _CLOCK)[0]
         self._word = 0
+        self._spec = (bytes(self._buf[_SHIP:_SHIP + 16]), self._clock, 0, self._world_sig)
         moved = (x, y) != old
         keep_int = fuel_was_int and not (action[0] == ActionType.MOVE_SHIP and moved)
         self._adopt(x, y, origin, dest, cargo, fuel, keep_int_fuel=keep_int)
@@ -268,22 +290,21 @@ class Environment:
             self.ship_position = [x, y]                                               # a fresh list, like :297
             self.np_game[old[0], old[1]] = Entity.TRAVEL                              # :303-304
             self.np_game[x, y] = Entity.BOAT
-        reward = float(h[_REWARD:_REWARD + 8].view(np.float64)[0])
-        done = bool(h[_DONE] & 1)
-        return self._build_state(), reward, done, {}
+        reward = _F64.unpack_from(self._buf, _REWARD)[0]
+        return self._build_state(), reward, bool(done_word & 1), {}
 
     # ------------------------------------------------------------------ extensions: MCTS on the device
-    def _root_tensor(self):
+    def _root_ptr(self):
         self._pack()
-        return self._dev[:16].clone().view(1, 16)
+        return self._ptr(_SHIP)      # the one root record is read from the host block in place
 
     def rollout_returns(self, simulations=50, max_rollout_steps=100, root_id=None):
         """``MCTSAgent._rollout`` (agents/mcts.py:211-238) x ``simulations`` from the current state in ONE launch
         (the reference builds an env copy and loops in Python for each).  Returns a list of floats."""
         ctx = self._sync_world()
-        roots = self._root_tensor()
+        roots = self._root_ptr()
         ret = torch.empty(simulations, dtype=torch.float64, device=self._device)
-        ctx.rollout(roots.data_ptr(), 1, simulations, max_rollout_steps, ret.data_ptr(), None, None, None,
+        ctx.rollout(roots, 1, simulations, max_rollout_steps, ret.data_ptr(), None, None, None,
                     self._seed, self._clock if root_id is None else root_id, self._stream())
         return ret.cpu().tolist()
 
@@ -293,7 +314,7 @@ class Environment:
         environment's format, ``[ActionType.MOVE_SHIP, [dx, dy]]``; falls back to ``sample_action()`` when the tree
         has no children or the state is not the four-move case, as the reference does (:291-292)."""
         ctx = self._sync_world()
-        roots = self._root_tensor()
+        roots = self._root_ptr()
         dev = self._device
         act = torch.empty(1, dtype=torch.int16, device=dev)
         visits = torch.empty(1, dtype=torch.int32, device=dev)
@@ -302,7 +323,7 @@ class Environment:
         ct = torch.empty(4, dtype=torch.float64, device=dev)
         st = torch.empty(1, dtype=torch.uint8, device=dev)
         log_table = np.concatenate([[0.0], np.log(np.arange(1, simulations + 2))])
-        ctx.mcts(roots.data_ptr(), 1, simulations, max_rollout_steps, c_param, log_table.ctypes.data, act.data_ptr(),
+        ctx.mcts(roots, 1, simulations, max_rollout_steps, c_param, log_table.ctypes.data, act.data_ptr(),
                  visits.data_ptr(), ca.data_ptr(), cv.data_ptr(), ct.data_ptr(), st.data_ptr(), self._seed,
                  self._clock if root_id is None else root_id, self._stream())
         a = int(act.item())

@@ -195,6 +195,41 @@ def test_agent_call_patterns(default_map):
     assert n_ok >= 8        # 4 moves + 4 selectable ports; takes are rejected once the ship left the port
 
 
+def test_sample_action_lookahead_is_invisible():
+    """step() draws the following sample_action() in the same launch (shipenv_step_sample).  The sequence of actions,
+    states and rewards must be the one obtained with a launch per sample_action(), also when attributes are edited
+    between the two calls (the look-ahead is then stale and must not be used) and across rejected steps."""
+    from shippingenv_b200 import _native
+    def run(lookahead, edits):
+        env = make_env(77, env_id=5)
+        env.reset()
+        trace, launches0 = [], _native.launch_count()
+        for t in range(300):
+            if not lookahead:
+                env._spec = None
+            if t in edits:
+                env.fuel = 150.5 if t % 2 else 33
+                env.cargo = 7
+            a = env.sample_action()
+            if t % 7 == 3 and env._get_current_port_idx() is None:
+                a = [4, 5] if t % 2 else [3, 5]           # TAKE_CARGO / TAKE_FUEL away from a port: rejected
+            try:
+                _, r, done, _ = env.step(a)
+            except Exception as e:
+                trace.append((t, repr(a), str(e)))
+                continue
+            trace.append((t, repr(a), bits(r), done, tuple(env.ship_position), env.cargo, bits(env.fuel), env._clock))
+            if done:
+                env.reset()
+        return trace, _native.launch_count() - launches0
+    edits = {40, 41, 90, 200}
+    plain, n_plain = run(False, edits)
+    fast, n_fast = run(True, edits)
+    assert plain == fast
+    assert any(len(row) == 3 for row in plain)            # rejected steps occurred (take at a port, off-map ...)
+    assert n_fast < 0.62 * n_plain                        # about one launch per pair instead of two
+
+
 def test_facade_mcts_extensions_match_batched_kernels():
     """Environment.rollout_returns / mcts_action are the R = 1 view of shipenv_rollout / shipenv_mcts."""
     from shippingenv_b200 import ActionType

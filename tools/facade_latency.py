@@ -32,3 +32,31 @@ for _ in range(2000):
     try: e.step([1, (0, 1)])
     except Exception: pass
 print(f"step only: {(time.perf_counter()-t)/2000*1e6:.0f} us")
+
+# the shape of MCTSAgent.choose_action in drop-in mode (agents/mcts.py:192-238): 50 simulations, each a fresh
+# instance with the attributes copied onto it, then up to 100 x (sample_action, step)
+e = make(); e.reset()
+t = time.perf_counter(); steps = 0
+for sim in range(50):
+    c = Environment(MAP, seed=sim)
+    c.port_positions = e.port_positions.copy(); c.port_fuel = e.port_fuel.copy(); c.port_cargo = e.port_cargo.copy()
+    c.ship_position = e.ship_position.copy(); c.cargo, c.fuel = e.cargo, e.fuel
+    c.origin_port_index, c.destination_port_index = e.origin_port_index, e.destination_port_index
+    c.np_game = e.np_game.copy()
+    done, k = False, 0
+    while not done and k < 100:
+        a = c.sample_action()
+        try:
+            _, r, done, _ = c.step(a); k += 1
+        except Exception:
+            continue
+    steps += k
+dt = time.perf_counter() - t
+print(f"MCTS-shaped decision through the facade (50 copies x <=100 sample+step): {dt*1e3:.0f} ms ({steps} steps); "
+      f"reference: 180-280 ms; Environment.mcts_action(): one launch")
+t = time.perf_counter()
+for _ in range(20): e.mcts_action()
+print(f"Environment.mcts_action(): {(time.perf_counter()-t)/20*1e3:.2f} ms per decision")
+t = time.perf_counter()
+for _ in range(50): e.rollout_returns()
+print(f"Environment.rollout_returns(): {(time.perf_counter()-t)/50*1e3:.2f} ms per 50 rollouts")
