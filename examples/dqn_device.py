@@ -10,6 +10,7 @@ a torch tensor, `shipenv_valid_actions` produces the mask, and nothing leaves th
 
     python examples/dqn_device.py --envs 1 --steps 2000        # the reference's loop shape: one env
     python examples/dqn_device.py --envs 4096 --steps 200      # the same agent over 4,096 envs
+    python examples/dqn_device.py --envs 1 --steps 5000 --graph   # one CUDA-graph replay per agent step
 """
 import argparse
 import os
@@ -37,7 +38,11 @@ class QNet(nn.Module):                      # agents/dqn.py:21-33
 
 
 def train(envs=1, steps=2000, seed=0, memory=2000, batch=32, gamma=0.95, lr=1e-3, eps_min=0.01, eps_decay=0.995,
-          max_steps=1000, target_every=10, device="cuda:0", map_npz=None, log=None):
+          max_steps=1000, target_every=10, device="cuda:0", map_npz=None, log=None, graph=False):
+    """Runs ``steps`` agent iterations over ``envs`` environments.  All loop state (replay ring head and fill,
+    epsilon, the current observation) lives in device tensors, so one iteration is a fixed sequence of launches:
+    with ``graph=True`` it is captured once in a CUDA graph (environment step, mask, action selection, replay write,
+    Q-update with a capturable Adam) and replayed, one host call per agent step."""
     torch.manual_seed(seed)
     z = np.load(map_npz or os.path.join(ROOT, "tests", "golden", "default_map.npz"))
     env = BatchedEnvironment(envs, passable=z["passable"], seed=seed, device=device, max_steps=max_steps,
@@ -46,18 +51,19 @@ def train(envs=1, steps=2000, seed=0, memory=2000, batch=32, gamma=0.95, lr=1e-3
     n_obs, n_act = env.obs_width, env.num_actions
     q, target = QNet(n_obs, n_act).to(device), QNet(n_obs, n_act).to(device)
     target.load_state_dict(q.state_dict())
-    opt = torch.optim.Adam(q.parameters(), lr=lr)
+    opt = torch.optim.Adam(q.parameters(), lr=lr, capturable=True)
     cap = max(memory, envs)                 # replay ring on the device
     mem_s = torch.zeros(cap, n_obs, device=device); mem_s2 = torch.zeros(cap, n_obs, device=device)
     mem_a = torch.zeros(cap, dtype=torch.long, device=device)
     mem_r = torch.zeros(cap, device=device); mem_d = torch.zeros(cap, device=device)
-    head, filled, eps, episodes_seen = 0, 0, 1.0, 0
+    head = torch.zeros((), dtype=torch.long, device=device)
+    filled = torch.zeros((), dtype=torch.long, device=device)
+    eps = torch.ones((), device=device)
+    loss_out = torch.zeros((), device=device)
     obs = env.observe().clone()
     ar = torch.arange(envs, device=device)
-    losses = []
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for it in range(steps):
+
+    def act_and_store():
         mask = env.valid_action_mask()                                   # [N, 259] bool, agents/dqn.py:189
         with torch.no_grad():
             qv = q(obs).masked_fill(~mask, -torch.inf)
@@ -70,30 +76,65 @@ def train(envs=1, steps=2000, seed=0, memory=2000, batch=32, gamma=0.95, lr=1e-3
         ok = ~unpack_bits(res.error_bits, envs)                          # e.g. select == origin: skipped, :309-311
         idx = (head + ar) % cap
         mem_s[idx], mem_a[idx], mem_r[idx], mem_s2[idx], mem_d[idx] = obs, action, res.reward, res.obs, done.float()
-        head, filled = (head + envs) % cap, min(filled + envs, cap)
-        obs = torch.where(ok[:, None], res.obs, obs).clone()
-        if filled >= batch:                                              # update(), :206-245
-            j = torch.randint(0, filled, (batch,), device=device)
-            cur = q(mem_s[j]).gather(1, mem_a[j, None]).squeeze(1)
-            with torch.no_grad():
-                tgt = mem_r[j] + gamma * target(mem_s2[j]).max(1)[0] * (1 - mem_d[j])
-            loss = nn.functional.mse_loss(cur, tgt)
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            opt.step()
-            eps = max(eps_min, eps * eps_decay)
-            if it % 50 == 0:
-                losses.append(loss.detach())
-        if it % 100 == 99:                                               # target sync every `target_every` episodes
+        head.add_(envs).remainder_(cap)
+        filled.add_(envs).clamp_(max=cap)
+        obs.copy_(torch.where(ok[:, None], res.obs, obs))
+
+    def update():                                                        # update(), :206-245
+        j = (torch.rand(batch, device=device) * filled).long()
+        cur = q(mem_s[j]).gather(1, mem_a[j, None]).squeeze(1)
+        with torch.no_grad():
+            tgt = mem_r[j] + gamma * target(mem_s2[j]).max(1)[0] * (1 - mem_d[j])
+        loss = nn.functional.mse_loss(cur, tgt)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        eps.mul_(eps_decay).clamp_(min=eps_min)
+        loss_out.copy_(loss.detach())
+
+    def iteration():
+        act_and_store()
+        update()
+
+    losses, episodes_seen = [], 0
+    fill_iters = min(steps, -(-batch // envs))     # iterations before the replay memory holds one batch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(fill_iters):
+        act_and_store()
+    it = fill_iters
+    replay = iteration
+    if graph and it + 3 < steps:
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):              # warm-up on a side stream, as torch's capture recipe asks
+            for _ in range(3):
+                iteration()
+        torch.cuda.current_stream(device).wait_stream(side)
+        it += 3
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            iteration()
+        it += 1
+        replay = g.replay
+    while it < steps:
+        replay()
+        it += 1
+        if it % 50 == 0:
+            losses.append(loss_out.clone())
+        if it % 100 == 0:                                                # target sync every `target_every` episodes
             n_ep = int(env.stats[3].item())
             if n_ep // target_every > episodes_seen // target_every:
                 target.load_state_dict(q.state_dict())
             episodes_seen = n_ep
+    if not losses:
+        losses.append(loss_out.clone())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    out = {"envs": envs, "iterations": steps, "agent_steps_per_s": envs * steps / dt, "iterations_per_s": steps / dt,
-           "final_epsilon": eps, "episodes": env.episode_summary(),
-           "loss_first_last": [float(losses[0]), float(losses[-1])] if losses else None}
+    out = {"envs": envs, "iterations": steps, "cuda_graph": bool(graph and replay is not iteration),
+           "agent_steps_per_s": envs * steps / dt, "iterations_per_s": steps / dt,
+           "final_epsilon": float(eps), "episodes": env.episode_summary(),
+           "loss_first_last": [float(losses[0]), float(losses[-1])]}
     if log:
         log(out)
     return out
@@ -104,6 +145,7 @@ if __name__ == "__main__":
     ap.add_argument("--envs", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--graph", action="store_true", help="capture one agent iteration in a CUDA graph and replay it")
     args = ap.parse_args()
     import json
-    print(json.dumps(train(args.envs, args.steps, args.seed)))
+    print(json.dumps(train(args.envs, args.steps, args.seed, graph=args.graph)))

@@ -17,9 +17,10 @@ def _load(name):
     return mod
 
 
-@pytest.mark.parametrize("envs,steps", [(1, 300), (512, 60)])
-def test_dqn_loop_on_device(envs, steps):
-    out = _load("dqn_device").train(envs=envs, steps=steps, max_steps=50)
+@pytest.mark.parametrize("envs,steps,graph", [(1, 300, False), (512, 60, False), (64, 200, True)])
+def test_dqn_loop_on_device(envs, steps, graph):
+    out = _load("dqn_device").train(envs=envs, steps=steps, max_steps=50, graph=graph)
+    assert out["cuda_graph"] == graph
     assert out["agent_steps_per_s"] > 0 and out["final_epsilon"] < 1.0
     assert all(math.isfinite(v) for v in out["loss_first_last"])
     if envs > 1:
