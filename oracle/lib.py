@@ -71,7 +71,9 @@ class Oracle:
     """A world (map + ports + constants) and the batched reference semantics over numpy arrays."""
 
     def __init__(self, passable, port_xy, port_fuel, port_cargo, **consts):
-        self.passable = np.ascontiguousarray(passable, dtype=np.uint8)
+        self.passable = np.array(passable, dtype=np.uint8, order="C")          # own copy
+        for x, y in port_xy:                                                   # add_port stamps Entity.PORT on the
+            self.passable[int(x), int(y)] = 1                                  # cell (env:65): never GROUND afterwards
         w = World()
         w.W, w.H = self.passable.shape
         w.P = len(port_xy)

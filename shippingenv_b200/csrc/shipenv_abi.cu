@@ -332,15 +332,16 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   const int64_t tiles = (n + kThreads - 1) / kThreads;
   const bool lean = !a.io.reward_f64 && !a.io.status && !a.io.taken && !a.io.ep_return;
   int grid = 0;
-  const bool fast_ok = a.io.done_bits && a.io.reset_bits && a.io.error_bits && (a.io.reward_f32 || !lean) && word0 == 0 &&
-                       c->P >= 2 && !c->no_fast_kernel;
   if (a.io.obs && (reinterpret_cast<uintptr_t>(a.io.obs) & 15u)) return fail(SHIPENV_E_ARG, "obs must be 16-byte aligned");
+  // throughput kernels: step_fast_kernel<policy, obs, envs per thread, lean>
+  constexpr int kEpt = SHIPENV_FAST_EPT;
+  const int ept = a.io.obs ? 1 : kEpt;
+  size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + (a.io.obs ? fast_smem_bytes<1>() : fast_smem_bytes<kEpt>());
+  if (a.io.obs) smem += 2 * size_t(kThreads) * a.obs_width * 4;
+  // with many ports two observation tiles of [256, 6+4P] floats do not fit: step_kernel then keeps one
+  const bool fast_ok = a.io.done_bits && a.io.reset_bits && a.io.error_bits && (a.io.reward_f32 || !lean) && word0 == 0 &&
+                       c->P >= 2 && !c->no_fast_kernel && smem <= size_t(c->max_smem_optin);
   if (fast_ok) {
-    // throughput kernels: step_fast_kernel<policy, obs, envs per thread, lean>
-    constexpr int kEpt = SHIPENV_FAST_EPT;
-    const int ept = a.io.obs ? 1 : kEpt;
-    size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + (a.io.obs ? fast_smem_bytes<1>() : fast_smem_bytes<kEpt>());
-    if (a.io.obs) smem += 2 * size_t(kThreads) * a.obs_width * 4;
     void (*kernel)(const StepArgs) = nullptr;
     const int variant = (all_policy ? 4 : 0) | (a.io.obs ? 2 : 0) | (lean ? 1 : 0);
     switch (variant) {

@@ -2,7 +2,7 @@
 arbitrary int16 actions, clocks near the 16-bit step boundary, all kernel variants -- CUDA vs the oracle."""
 import numpy as np
 import pytest
-from hypothesis import HealthCheck, given, settings, strategies as st
+from hypothesis import HealthCheck, example, given, settings, strategies as st
 
 from conftest import golden
 from oracle import lib as orc
@@ -89,3 +89,85 @@ def test_rollouts_from_arbitrary_roots(seed, S, L):
     assert (out["steps"].cpu().numpy() == steps).all()
     assert (out["returns"].cpu().numpy().view(np.uint64) == want.view(np.uint64)).all()
     assert out["final"].cpu().numpy().tobytes() == fin.tobytes()
+
+
+def random_world(rng, W, H, P, density):
+    """Random passability, P distinct port cells (fewer if the map is smaller), random stock."""
+    passable = (rng.random((W, H)) < density).astype(np.uint8)
+    P = min(P, W * H)
+    cells = rng.choice(W * H, size=P, replace=False)
+    if P and rng.random() < 0.5:
+        cells[0] = rng.choice([0, W * H - 1, H - 1, (W - 1) * H])      # a port in a corner of the map
+        cells = np.array(list(dict.fromkeys(cells.tolist())))
+    ports = [[int(c) // H, int(c) % H] for c in cells]
+    fuel = rng.integers(0, 256, len(ports)).tolist()
+    cargo = rng.integers(0, 256, len(ports)).tolist()
+    return passable, ports, fuel, cargo
+
+
+def world_population(rng, n, W, H, ports):
+    P = len(ports)
+    s = np.zeros(n, orc.SHIP_DTYPE)
+    s["x"], s["y"] = rng.integers(0, W, n), rng.integers(0, H, n)
+    if P:
+        on_port = rng.random(n) < 0.4
+        k = rng.integers(0, P, n)
+        s["x"] = np.where(on_port, np.array(ports)[k, 0], s["x"])
+        s["y"] = np.where(on_port, np.array(ports)[k, 1], s["y"])
+    idx = np.arange(P).tolist() + [255]
+    s["origin"], s["dest"] = rng.choice(idx, n), rng.choice(idx, n)
+    s["cargo"] = rng.choice([0, 0, 1, 7, 49, 50, 51, 300, -2], n)
+    s["fuel"] = np.where(rng.random(n) < 0.3, rng.choice(FUEL_EDGES, n), rng.random(n) * 60)
+    clock = (rng.integers(0, 1 << 16, n).astype(np.uint32) << np.uint32(16)) | rng.integers(0, 40, n).astype(np.uint32)
+    return s, clock
+
+
+@settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2**63 - 1), W=st.sampled_from([1, 2, 31, 32, 33, 100, 255, 256]),
+       H=st.sampled_from([1, 2, 31, 32, 33, 64, 65, 100, 255, 256]), P=st.sampled_from([0, 1, 2, 3, 5, 17, 31, 32]),
+       density=st.sampled_from([0.0, 0.3, 0.9, 1.0]), n=st.sampled_from([1, 300, 2049]), lean=st.booleans())
+@example(seed=1, W=256, H=256, P=32, density=0.9, n=2049, lean=False)     # largest world, 134-float observation rows
+@example(seed=2, W=256, H=256, P=32, density=0.9, n=2049, lean=True)
+@example(seed=3, W=33, H=255, P=31, density=0.3, n=300, lean=False)
+@example(seed=4, W=1, H=1, P=1, density=0.0, n=300, lean=False)          # the smallest world
+@example(seed=5, W=256, H=1, P=2, density=1.0, n=2049, lean=True)        # one column: every N/S move leaves the map
+@example(seed=6, W=2, H=256, P=17, density=1.0, n=1, lean=False)
+def test_steps_on_arbitrary_worlds(seed, W, H, P, density, n, lean):
+    """Map sizes 1..256 on both axes (bitmap rows of 1..8 words), 0..32 ports (observation rows of 6..134 floats),
+    ports on the border, all-ground and all-water maps: eight steps of mixed actions, CUDA vs the oracle."""
+    import torch
+    from shippingenv_b200 import BatchedEnvironment, unpack_bits
+    rng = np.random.default_rng(seed % (1 << 32))
+    passable, ports, pf, pc = random_world(rng, W, H, P, density)
+    P = len(ports)
+    auto_reset = P >= 2
+    env = BatchedEnvironment(n, passable=passable, ports=ports, port_fuel=pf, port_cargo=pc, seed=seed,
+                             device="cuda:0", max_steps=37, auto_reset=auto_reset)
+    o = orc.Oracle(passable, ports, pf, pc)
+    ships, clock = world_population(rng, n, W, H, ports)
+    env.load_state(ships, clock)
+    n_act = 4 + P + 250
+    for t in range(8):
+        kind = rng.random(n)
+        acts = np.where(kind < 0.5, rng.integers(0, 4, n), np.where(kind < 0.75, -1, rng.integers(0, n_act + 2, n)))
+        acts = acts.astype(np.int16)
+        a = torch.from_numpy(acts).cuda()
+        if lean:
+            r = env.step(a)
+        else:
+            r = env.step(a, want_status=True, want_taken=True, want_reward64=True, want_obs=True)
+        ref = o.step(ships, clock, acts, seed, 0, 37, auto_reset, 0)
+        g_ships, g_clock = env.state_numpy()
+        bad = np.nonzero((g_ships != ships.view(np.uint8).reshape(n, 16)).any(1))[0]
+        assert bad.size == 0, (t, bad[:5], acts[bad[:5]], g_ships[bad[:5]], ships[bad[:5]])
+        assert (g_clock == clock).all(), t
+        assert (r.reward.cpu().numpy() == ref["reward"].astype(np.float32)).all(), t
+        assert (unpack_bits(r.done_bits, n).cpu().numpy() == ref["done"].astype(bool)).all(), t
+        assert (unpack_bits(r.reset_bits, n).cpu().numpy() == ref["reset"].astype(bool)).all(), t
+        assert (unpack_bits(r.error_bits, n).cpu().numpy() == (ref["status"] != 0)).all(), t
+        if not lean:
+            assert (r.status.cpu().numpy() == ref["status"]).all(), t
+            assert (r.reward64.cpu().numpy().view(np.uint64) == ref["reward"].view(np.uint64)).all(), t
+            assert (r.obs.cpu().numpy().view(np.uint32) == o.observe(ships).view(np.uint32)).all(), t
+    if P >= 1:
+        assert (env.valid_action_mask().cpu().numpy() == o.valid_actions(ships).astype(bool)).all()
