@@ -171,3 +171,35 @@ def test_steps_on_arbitrary_worlds(seed, W, H, P, density, n, lean):
             assert (r.obs.cpu().numpy().view(np.uint32) == o.observe(ships).view(np.uint32)).all(), t
     if P >= 1:
         assert (env.valid_action_mask().cpu().numpy() == o.valid_actions(ships).astype(bool)).all()
+
+
+@settings(max_examples=16, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2**63 - 1), W=st.sampled_from([1, 2, 33, 100, 256]), H=st.sampled_from([1, 2, 31, 100, 256]),
+       P=st.sampled_from([0, 1, 2, 5, 32]), density=st.sampled_from([0.0, 0.5, 1.0]))
+@example(seed=9, W=256, H=256, P=32, density=0.9)
+@example(seed=10, W=1, H=2, P=1, density=0.0)
+def test_rollouts_and_mcts_on_arbitrary_worlds(seed, W, H, P, density):
+    """MCTSAgent._rollout and choose_action from arbitrary roots in arbitrary worlds (including the ones where nothing
+    can move and the ones without ports), CUDA vs the oracle."""
+    from shippingenv_b200 import BatchedEnvironment
+    rng = np.random.default_rng(seed % (1 << 32))
+    passable, ports, pf, pc = random_world(rng, W, H, P, density)
+    R = 200
+    env = BatchedEnvironment(R, passable=passable, ports=ports, port_fuel=pf, port_cargo=pc, seed=seed,
+                             device="cuda:0", auto_reset=False)
+    o = orc.Oracle(passable, ports, pf, pc)
+    roots, _ = world_population(rng, R, W, H, ports)
+    env.load_state(roots)
+    out = env.rollout(3, 17, root_id_base=5, want_final=True)
+    want, fin, steps, status = o.rollout(roots, 3, 17, seed, 5)
+    assert (out["status"].cpu().numpy() == status).all()
+    assert (out["steps"].cpu().numpy() == steps).all()
+    assert (out["returns"].cpu().numpy().view(np.uint64) == want.view(np.uint64)).all()
+    assert out["final"].cpu().numpy().tobytes() == fin.tobytes()
+    got = {k: v.cpu().numpy() for k, v in env.mcts(12, 10, root_id_base=3).items()}
+    ref = orc.mcts(o, roots, 12, 10, seed, 3)
+    assert (got["status"] == ref["status"]).all()
+    ok = ref["status"] == 0
+    for k in ("action", "root_visits", "child_action", "child_visits"):
+        assert (got[k][ok] == ref[k][ok]).all(), k
+    assert (got["child_total"][ok].view(np.uint64) == ref["child_total"][ok].view(np.uint64)).all()
