@@ -156,6 +156,9 @@ class BatchedEnvironment:
         key = (want_obs, want_status, want_taken, want_reward64, None if obs_out is None else obs_out.data_ptr())
         cached = self._step_cache.get(key)
         if cached is None:
+            if len(self._step_cache) >= 64:        # a caller cycling through many obs_out buffers: start over
+                self._step_cache.clear()
+                self._io_keepalive.clear()
             cached = self._step_cache[key] = self._build_step_io(want_obs, want_status, want_taken, want_reward64,
                                                                  obs_out)
         io_ref, res = cached

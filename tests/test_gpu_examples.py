@@ -25,3 +25,12 @@ def test_dqn_loop_on_device(envs, steps, graph):
     assert all(math.isfinite(v) for v in out["loss_first_last"])
     if envs > 1:
         assert out["episodes"]["total_episodes"] > 0
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_sarsa_loop_on_device(graph):
+    """tabular SARSA over N envs, keys from shipenv_discretize, Q-table in HBM."""
+    out = _load("sarsa_device").train(envs=2048, steps=80, max_steps=40, graph=graph)
+    assert out["cuda_graph"] == graph and out["agent_steps_per_s"] > 0
+    assert out["states_visited"] > 100 and math.isfinite(out["mean_abs_td_last"]) and out["mean_abs_td_last"] > 0
+    assert out["episodes"]["total_episodes"] > 0 and out["epsilon"] < 1.0
