@@ -34,3 +34,12 @@ def test_sarsa_loop_on_device(graph):
     assert out["cuda_graph"] == graph and out["agent_steps_per_s"] > 0
     assert out["states_visited"] > 100 and math.isfinite(out["mean_abs_td_last"]) and out["mean_abs_td_last"] > 0
     assert out["episodes"]["total_episodes"] > 0 and out["epsilon"] < 1.0
+
+
+def test_mcts_agent_on_device_beats_the_random_policy():
+    """BASELINE config 4 as an agent: choose_action for every ship each step, against sample_action."""
+    mod = _load("mcts_device")
+    planned = mod.play(envs=512, steps=40, simulations=20, rollout_steps=30)
+    rand = mod.play(envs=512, steps=40, planner=False)
+    assert planned["decisions_per_s"] > 0
+    assert planned["mean_reward_per_step"] > rand["mean_reward_per_step"]
