@@ -113,8 +113,10 @@ class Environment:
 
     # ------------------------------------------------------------------ host <-> device
     def _sync_world(self):
-        key = (id(self.np_game), len(self.port_positions))
-        if key != self._passable_key:
+        # keyed on the array object itself (held, so its id cannot be recycled) and the port count: the passable set
+        # only changes when np_game is replaced or add_port stamps a cell (it never shrinks)
+        key = (self.np_game, len(self.port_positions))
+        if self._passable_key is None or key[0] is not self._passable_key[0] or key[1] != self._passable_key[1]:
             g = np.asarray(self.np_game)
             if g.ndim != 2 or g.shape[0] < self.size_game[0] or g.shape[1] < self.size_game[1]:
                 raise ValueError("np_game does not cover size_game (non-square maps are not supported)")
