@@ -10,9 +10,9 @@ done or after 1,000 steps, Philox seed 0x5EED, global env ids rank * 2^21 + i (w
 collective on the step path).  One "step" = one shipenv_step launch over every env of the rank.
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM (4 env groups
-per GPU stepped round-robin so that the working set exceeds L2); `e2e` goes through the same C-ABI call with the step's actions coming
-from pinned host memory and reward + done/reset masks going back to it, copies inside the timed
-region.  `--impl reference` times the CPU oracle port (oracle/shipenv_oracle.c, the reference
+per GPU stepped round-robin so that the working set exceeds L2); `e2e` goes through the C-ABI call that takes
+HOST buffers (shipenv_step_host): the step's actions come from pinned host memory and reward + done / reset /
+error masks go back to it, copies inside the timed region.  `--impl reference` times the CPU oracle port (oracle/shipenv_oracle.c, the reference
 is pure Python and cannot travel to the GPU box) on all host cores on the same workload.
 """
 import argparse
@@ -327,20 +327,14 @@ def run_ours(args):
     nw = (n + 31) // 32
     streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
     h_act = [torch.randint(0, 4, (n,), dtype=torch.int16).pin_memory() for _ in range(G)]
-    d_act = [torch.empty(n, dtype=torch.int16, device=dev) for _ in range(G)]
     h_reward = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(G)]
-    h_done = [torch.empty(nw, dtype=torch.int32).pin_memory() for _ in range(G)]
-    h_reset = [torch.empty(nw, dtype=torch.int32).pin_memory() for _ in range(G)]
+    h_masks = [[torch.empty(nw, dtype=torch.int32).pin_memory() for _ in range(3)] for _ in range(G)]
     Ke = max(8, min(K, 128))
 
-    def e2e_step(t):
+    def e2e_step(t):        # shipenv_step_host: host actions in, host reward + done / reset / error masks out
         g = t % G
         with torch.cuda.stream(streams[g]):
-            d_act[g].copy_(h_act[g], non_blocking=True)
-            r = envs[g].step(d_act[g])
-            h_reward[g].copy_(r.reward, non_blocking=True)
-            h_done[g].copy_(r.done_bits, non_blocking=True)
-            h_reset[g].copy_(r.reset_bits, non_blocking=True)
+            envs[g].step_host(h_act[g], h_reward[g], *h_masks[g])
 
     for t in range(2 * G):
         e2e_step(t)
@@ -436,10 +430,11 @@ def run_ours(args):
                          "kernel": "shipenv::step_fast_kernel",
                          "algorithmic_bytes_per_launch": n * BYTES_PER_STEP},
             "e2e": {"value": n_total * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s",
-                    "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n + 8 * nw, "steps": Ke,
-                    "what": "shipenv_step via BatchedEnvironment.step: int16 actions from pinned host memory, f32 reward "
-                            "+ done/reset masks to pinned host memory; one stream per env group so that copies "
-                            "overlap kernels"},
+                    "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n + 12 * nw, "steps": Ke,
+                    "what": "shipenv_step_host (BatchedEnvironment.step_host): the C-ABI call takes int16 actions from "
+                            "page-locked host memory and delivers f32 reward + done/reset/error masks to page-locked "
+                            "host memory, pipelining copy-in / kernel / copy-out of 1 Mi-env chunks; env groups "
+                            "round-robin on one stream each"},
             "gpu_launches": launches, "host_us_per_launch": host_us, "clocks": clocks.summary(), "cpus_pinned_to_gpu_numa_node": numa,
             "rejected_actions_last_step": err, "reward_checksum": checksum,
         }

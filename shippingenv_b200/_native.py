@@ -69,6 +69,10 @@ _SIGNATURES = {
     "shipenv_step_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(StepIO), C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_uint32,
                                       C.c_uint32, C.c_void_p]),
+    "shipenv_step_host_workspace": (C.c_size_t, [C.c_int64]),
+    "shipenv_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int64, C.c_int,
+                                    C.c_uint32, C.c_void_p]),
     "shipenv_sample_action": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]),
     "shipenv_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -210,6 +214,11 @@ class Context:
                     max_steps, flags, word0, stream):
         check(lib().shipenv_step_sample(self._h, ships, clock, actions, C.byref(io), next_action, next_words,
                                         next_status, seed, env_id_base, n, max_steps, flags, word0, stream))
+
+    def step_host(self, ships, clock, h_actions, h_reward, h_done, h_reset, h_error, workspace, workspace_bytes, seed,
+                  env_id_base, n, max_steps, flags, stream):
+        check(lib().shipenv_step_host(self._h, ships, clock, h_actions, h_reward, h_done, h_reset, h_error, workspace,
+                                      workspace_bytes, seed, env_id_base, n, max_steps, flags, stream))
 
     def synchronize(self, stream):
         check(lib().shipenv_stream_synchronize(self._h, stream))

@@ -100,6 +100,7 @@ class BatchedEnvironment:
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
             self.stats = new_stats(dev)
         self._policy = None
+        self._host_out = self._host_ws = None
         self.stream, self._stream_handle = None, None
         self._step_cache, self._io_keepalive = {}, []
         self._lib_step = nat.lib().shipenv_step
@@ -196,6 +197,35 @@ class BatchedEnvironment:
             io.ep_return, io.stats = self.ep_return.data_ptr(), self.stats.data_ptr()
         self._io_keepalive.append(io)
         return ctypes.byref(io), res
+
+    def step_host(self, actions, reward=None, done_bits=None, reset_bits=None, error_bits=None):
+        """``Environment.step`` for every env with the actions in HOST memory and the results delivered to HOST memory
+        (``shipenv_step_host``): ``actions`` is an int16 CPU tensor [N]; ``reward`` float32 [N] and the three int32
+        ballot arrays [ceil(N/32)] are CPU tensors that are filled in place (allocated page-locked on first use when
+        not given).  Copies and kernels of successive chunks of the batch are pipelined inside the call; it is
+        asynchronous with respect to the host when the buffers are page-locked -- synchronise the stream before
+        reading them."""
+        if actions.dtype != torch.int16 or actions.device.type != "cpu" or actions.numel() != self.n \
+                or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous int16 CPU tensor of shape [num_envs]")
+        nw = (self.n + 31) // 32
+        if self._host_out is None:
+            self._host_out = (torch.empty(self.n, dtype=torch.float32).pin_memory(),
+                              torch.empty(nw, dtype=torch.int32).pin_memory(),
+                              torch.empty(nw, dtype=torch.int32).pin_memory(),
+                              torch.empty(nw, dtype=torch.int32).pin_memory())
+            size = nat.lib().shipenv_step_host_workspace(self.n)
+            self._host_ws = torch.empty(size, dtype=torch.uint8, device=self.device)
+        outs = [given if given is not None else own
+                for given, own in zip((reward, done_bits, reset_bits, error_bits), self._host_out)]
+        for t, (dt, k) in zip(outs, ((torch.float32, self.n), (torch.int32, nw), (torch.int32, nw), (torch.int32, nw))):
+            if t.dtype != dt or t.device.type != "cpu" or t.numel() != k or not t.is_contiguous():
+                raise ValueError("host outputs must be contiguous CPU tensors: float32 [N], int32 [ceil(N/32)] x 3")
+        flags = nat.F_AUTO_RESET if self.auto_reset else 0
+        self.ctx.step_host(self._ships_ptr, self._clock_ptr, actions.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
+                           outs[2].data_ptr(), outs[3].data_ptr(), self._host_ws.data_ptr(), self._host_ws.numel(),
+                           self.seed, self.env_id_base, self.n, self.max_steps, flags, self._stream())
+        return StepResult(*outs)
 
     def capture_steps(self, actions, **kw):
         """Capture ``len(actions)`` consecutive steps (``actions``: int16 [T, N], one row per step) into a CUDA

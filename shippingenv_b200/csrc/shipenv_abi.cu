@@ -2,6 +2,7 @@
 // Host logic only; all arithmetic of the hot path is in kernels.cuh / transition.cuh.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -53,6 +54,10 @@ const shipenv_consts kDefaultConsts = {
 
 }  // namespace
 
+constexpr int kHostStreams = 4;                 // chunks of one shipenv_step_host call in flight
+constexpr int kTicketSlots = 1 + kHostStreams;   // slot 0: shipenv_step; 1..: the chunks
+constexpr int kTicketStride = 32;                // uint32 words between counters
+
 struct shipenv_ctx {
   int device = 0;
   int sm_count = 0;
@@ -65,7 +70,13 @@ struct shipenv_ctx {
   // device blob
   void* d_world = nullptr;
   double* d_log_table = nullptr;        // shipenv_mcts: log(n), n = 0..SHIPENV_MCTS_MAX_SIMS+1
-  uint32_t* d_tile_counter = nullptr;   // ticket counter of step_fast_kernel's tile scheduler (self-resetting)
+  uint32_t* d_tile_counter = nullptr;   // ticket counters of step_fast_kernel's tile scheduler (self-resetting), one
+                                        // per launch that may be in flight at a time, 128 bytes apart
+  // shipenv_step_host: internal streams and events, created on first use
+  cudaStream_t host_stream[kHostStreams] = {};
+  cudaEvent_t host_fork = nullptr, host_join[kHostStreams] = {};
+  bool host_ready = false;
+  int host_chunks = kHostStreams;       // SHIPENV_HOST_CHUNKS=1..4 (tuning): chunks per shipenv_step_host call
   std::vector<unsigned char> h_world;
   uint32_t world_bytes = 0;
   bool dirty = true;
@@ -220,14 +231,15 @@ int shipenv_ctx_create(int device, shipenv_ctx** out) {
   if (!c) return fail(SHIPENV_E_ARG, "out of host memory");
   c->device = device;
   { const char* e = getenv("SHIPENV_NO_FAST"); c->no_fast_kernel = e && e[0] == '1'; }
+  { const char* e = getenv("SHIPENV_HOST_CHUNKS"); if (e && e[0] >= '1' && e[0] <= '0' + kHostStreams) c->host_chunks = e[0] - '0'; }
   CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   cudaError_t e = cudaMalloc(&c->d_world, kMaxWorldBytes);
   if (e != cudaSuccess) { delete c; return fail(SHIPENV_E_CUDA, "cudaMalloc(world): %s", cudaGetErrorString(e)); }
   e = cudaMalloc(&c->d_log_table, sizeof(double) * (SHIPENV_MCTS_MAX_SIMS + 2));
   if (e != cudaSuccess) { cudaFree(c->d_world); delete c; return fail(SHIPENV_E_CUDA, "log table: %s", cudaGetErrorString(e)); }
-  e = cudaMalloc(&c->d_tile_counter, 256);
-  if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, 256);
+  e = cudaMalloc(&c->d_tile_counter, kTicketSlots * kTicketStride * 4);
+  if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, kTicketSlots * kTicketStride * 4);
   if (e != cudaSuccess) { cudaFree(c->d_world); delete c; return fail(SHIPENV_E_CUDA, "tile counter: %s", cudaGetErrorString(e)); }
   *out = c;
   return 0;
@@ -240,6 +252,10 @@ int shipenv_ctx_destroy(shipenv_ctx* c) {
     if (c->d_world) cudaFree(c->d_world);
     if (c->d_tile_counter) cudaFree(c->d_tile_counter);
     if (c->d_log_table) cudaFree(c->d_log_table);
+    if (c->host_ready) {
+      for (int k = 0; k < kHostStreams; ++k) { cudaStreamDestroy(c->host_stream[k]); cudaEventDestroy(c->host_join[k]); }
+      cudaEventDestroy(c->host_fork);
+    }
   }
   delete c;
   return 0;
@@ -307,9 +323,11 @@ int shipenv_reset(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, uint64_t
   return 0;
 }
 
-int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* actions,
-                 const shipenv_step_io* io, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
-                 uint32_t flags, uint32_t word0, void* stream_) {
+// shipenv_step proper.  `ticket_slot` selects the tile-ticket counter: launches that may run concurrently on one
+// context (the chunks of shipenv_step_host) must not share one.
+static int step_impl(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* actions,
+                     const shipenv_step_io* io, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
+                     uint32_t flags, uint32_t word0, cudaStream_t stream, int ticket_slot) {
   if (int rc = check_ctx(c)) return rc;
   const bool all_policy = flags & SHIPENV_F_ALL_POLICY;
   if (n < 0 || (n > 0 && (!ships || !clock || (!actions && !all_policy)))) return fail(SHIPENV_E_ARG, "step: null buffer or negative n");
@@ -320,7 +338,6 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
     return fail(SHIPENV_E_ARG, "step: ships, clock and actions must be 16-byte aligned (TMA bulk copies)");
   if ((flags & SHIPENV_F_AUTO_RESET) && c->P < 2) return fail(SHIPENV_E_STATE, "auto-reset needs at least 2 ports");
   DeviceGuard guard(c->device);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = sync_world(c, stream)) return rc;
   StepArgs a{};
   a.world = c->d_world; a.world_bytes = c->world_bytes;
@@ -357,7 +374,7 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
     shipenv_ctx::Occ* occ = &c->occ_fast[variant];
     const int64_t fast_tiles = (n + int64_t(kThreads) * ept - 1) / (int64_t(kThreads) * ept);
     if (int rc = grid_for(c, kernel, *occ, kStepBlock, smem, fast_tiles, &grid)) return rc;
-    a.tile_counter = c->d_tile_counter;
+    a.tile_counter = c->d_tile_counter + ticket_slot * kTicketStride;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStepBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -391,6 +408,81 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
   }
   CUDA_TRY(cudaGetLastError());
   ++g_launches;
+  return 0;
+}
+
+int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* actions,
+                 const shipenv_step_io* io, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
+                 uint32_t flags, uint32_t word0, void* stream_) {
+  return step_impl(c, ships, clock, actions, io, seed, env_id_base, n, max_steps, flags, word0,
+                   static_cast<cudaStream_t>(stream_), 0);
+}
+
+size_t shipenv_step_host_workspace(int64_t n) {
+  if (n <= 0) return 0;
+  const size_t nw = (size_t(n) + 31) / 32;
+  // actions (2 B) and rewards (4 B) per env, three mask arrays; every array starts 256-byte aligned
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  return up(size_t(n) * 2) + up(size_t(n) * 4) + 3 * up(nw * 4);
+}
+
+int shipenv_step_host(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* h_actions,
+                      float* h_reward, uint32_t* h_done_bits, uint32_t* h_reset_bits, uint32_t* h_error_bits,
+                      void* workspace, size_t workspace_bytes, uint64_t seed, uint64_t env_id_base, int64_t n,
+                      int max_steps, uint32_t flags, void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  if (n < 0 || (n > 0 && (!ships || !clock || !h_actions || !h_reward || !workspace)))
+    return fail(SHIPENV_E_ARG, "step_host: null buffer or negative n");
+  if (n == 0) return 0;
+  if (workspace_bytes < shipenv_step_host_workspace(n) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return fail(SHIPENV_E_ARG, "step_host: workspace needs %zu bytes, 256-byte aligned", shipenv_step_host_workspace(n));
+  if (flags & SHIPENV_F_ALL_POLICY) return fail(SHIPENV_E_ARG, "step_host: actions come from the host; SHIPENV_F_ALL_POLICY makes no sense here");
+  DeviceGuard guard(c->device);
+  cudaStream_t user = static_cast<cudaStream_t>(stream_);
+  if (!c->host_ready) {
+    CUDA_TRY(cudaEventCreateWithFlags(&c->host_fork, cudaEventDisableTiming));
+    for (int k = 0; k < kHostStreams; ++k) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&c->host_stream[k], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&c->host_join[k], cudaEventDisableTiming));
+    }
+    c->host_ready = true;
+  }
+  if (int rc = sync_world(c, user)) return rc;     // before the fork: every chunk sees the uploaded world
+  const size_t nw = (size_t(n) + 31) / 32;
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  int16_t* d_act = reinterpret_cast<int16_t*>(ws);
+  float* d_reward = reinterpret_cast<float*>(ws + up(size_t(n) * 2));
+  uint32_t* d_mask[3];
+  d_mask[0] = reinterpret_cast<uint32_t*>(ws + up(size_t(n) * 2) + up(size_t(n) * 4));
+  d_mask[1] = d_mask[0] + up(nw * 4) / 4;
+  d_mask[2] = d_mask[1] + up(nw * 4) / 4;
+  // Chunks of whole 512-env tiles (so mask words, TMA alignment and tile boundaries all fall on chunk boundaries), at
+  // least 1 Mi envs each (a copy of less than ~2 MB does not reach PCIe speed).  Chunk 0 runs on the caller's stream,
+  // the others on internal streams forked from it and joined back: a one-chunk call involves no other stream.
+  constexpr int64_t kGrain = 512, kMinChunk = 1 << 20;
+  int chunks = int(std::min<int64_t>(c->host_chunks, std::max<int64_t>(1, n / kMinChunk)));
+  const int64_t per = ((n + chunks - 1) / chunks + kGrain - 1) / kGrain * kGrain;
+  chunks = int((n + per - 1) / per);
+  if (chunks > 1) CUDA_TRY(cudaEventRecord(c->host_fork, user));
+  for (int k = chunks - 1; k >= 0; --k) {            // internal streams first, the caller's stream last
+    const int64_t lo = int64_t(k) * per, len = std::min<int64_t>(per, n - lo);
+    cudaStream_t s = k == 0 ? user : c->host_stream[k];
+    if (k > 0) CUDA_TRY(cudaStreamWaitEvent(s, c->host_fork, 0));
+    CUDA_TRY(cudaMemcpyAsync(d_act + lo, h_actions + lo, size_t(len) * 2, cudaMemcpyHostToDevice, s));
+    shipenv_step_io io{};
+    io.reward_f32 = d_reward + lo;
+    io.done_bits = d_mask[0] + lo / 32; io.reset_bits = d_mask[1] + lo / 32; io.error_bits = d_mask[2] + lo / 32;
+    if (int rc = step_impl(c, ships + lo, clock + lo, d_act + lo, &io, seed, env_id_base + uint64_t(lo), len, max_steps,
+                           flags, 0u, s, 1 + k))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_reward + lo, d_reward + lo, size_t(len) * 4, cudaMemcpyDeviceToHost, s));
+    if (k > 0) CUDA_TRY(cudaEventRecord(c->host_join[k], s));
+  }
+  for (int k = 1; k < chunks; ++k) CUDA_TRY(cudaStreamWaitEvent(user, c->host_join[k], 0));
+  uint32_t* h_mask[3] = {h_done_bits, h_reset_bits, h_error_bits};
+  for (int m = 0; m < 3; ++m)
+    if (h_mask[m]) CUDA_TRY(cudaMemcpyAsync(h_mask[m], d_mask[m], nw * 4, cudaMemcpyDeviceToHost, user));
   return 0;
 }
 

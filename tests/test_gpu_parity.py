@@ -412,3 +412,34 @@ def test_cuda_graph_replay_of_steps(torch_cuda, default_map):
         torch.cuda.synchronize()
         assert torch.equal(eager.ships, graphed.ships) and torch.equal(eager.clock, graphed.clock), rep
         assert torch.equal(eager.reward, graphed.reward) and torch.equal(eager.reset_bits, graphed.reset_bits)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 600_001, 2_097_152 + 700, 4_500_000])
+def test_cuda_step_host_equals_step(torch_cuda, default_map, n):
+    """shipenv_step_host (host actions in, host reward + masks out, chunks pipelined on internal streams) gives what
+    shipenv_step gives on the same states; page-locked and pageable host buffers both work."""
+    import torch
+    from shippingenv_b200 import BatchedEnvironment
+    envs = [BatchedEnvironment(n, passable=default_map["passable"], seed=77, device="cuda:0", max_steps=40,
+                               env_id_base=5) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    gen = torch.Generator().manual_seed(n)
+    for t in range(6):
+        acts = torch.randint(0, 4, (n,), generator=gen, dtype=torch.int16)
+        if t % 3 == 2:
+            acts[::7] = -1                                     # policy actions travel through the host path as well
+            acts[3::11] = 4 + (t % 5)
+        want = envs[0].step(acts.cuda())
+        host_acts = acts.pin_memory() if t % 2 == 0 else acts
+        if t == 4:      # caller-provided pageable outputs
+            outs = (torch.empty(n, dtype=torch.float32), *(torch.empty((n + 31) // 32, dtype=torch.int32) for _ in range(3)))
+            got = envs[1].step_host(host_acts, *outs)
+        else:
+            got = envs[1].step_host(host_acts)
+        torch.cuda.synchronize()
+        assert torch.equal(got.reward, want.reward.cpu()), t
+        assert torch.equal(got.done_bits, want.done_bits.cpu()), t
+        assert torch.equal(got.reset_bits, want.reset_bits.cpu()), t
+        assert torch.equal(got.error_bits, want.error_bits.cpu()), t
+        assert torch.equal(envs[0].ships, envs[1].ships) and torch.equal(envs[0].clock, envs[1].clock), t
