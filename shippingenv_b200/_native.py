@@ -72,7 +72,7 @@ _SIGNATURES = {
     "shipenv_step_host_workspace": (C.c_size_t, [C.c_int64]),
     "shipenv_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int64, C.c_int,
-                                    C.c_uint32, C.c_void_p]),
+                                    C.c_uint32, C.c_int, C.c_void_p]),
     "shipenv_sample_action": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]),
     "shipenv_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -216,9 +216,9 @@ class Context:
                                         next_status, seed, env_id_base, n, max_steps, flags, word0, stream))
 
     def step_host(self, ships, clock, h_actions, h_reward, h_done, h_reset, h_error, workspace, workspace_bytes, seed,
-                  env_id_base, n, max_steps, flags, stream):
+                  env_id_base, n, max_steps, flags, chunks, stream):
         check(lib().shipenv_step_host(self._h, ships, clock, h_actions, h_reward, h_done, h_reset, h_error, workspace,
-                                      workspace_bytes, seed, env_id_base, n, max_steps, flags, stream))
+                                      workspace_bytes, seed, env_id_base, n, max_steps, flags, chunks, stream))
 
     def synchronize(self, stream):
         check(lib().shipenv_stream_synchronize(self._h, stream))

@@ -198,22 +198,31 @@ class BatchedEnvironment:
         self._io_keepalive.append(io)
         return ctypes.byref(io), res
 
-    def step_host(self, actions, reward=None, done_bits=None, reset_bits=None, error_bits=None):
+    def host_buffers(self):
+        """Page-locked host outputs for :meth:`step_host`, carved from one allocation in the order ``reward`` float32 [N],
+        ``done_bits``, ``reset_bits``, ``error_bits`` int32 [ceil(N/32)] -- laid out like this they come back with a
+        single device-to-host copy."""
+        nw = (self.n + 31) // 32
+        block = torch.empty(4 * self.n + 12 * nw, dtype=torch.uint8).pin_memory()
+        reward = block[:4 * self.n].view(torch.float32)
+        masks = block[4 * self.n:].view(torch.int32)
+        return reward, masks[:nw], masks[nw:2 * nw], masks[2 * nw:]
+
+    def step_host(self, actions, reward=None, done_bits=None, reset_bits=None, error_bits=None, chunks=0):
         """``Environment.step`` for every env with the actions in HOST memory and the results delivered to HOST memory
         (``shipenv_step_host``): ``actions`` is an int16 CPU tensor [N]; ``reward`` float32 [N] and the three int32
         ballot arrays [ceil(N/32)] are CPU tensors that are filled in place (allocated page-locked on first use when
-        not given).  Copies and kernels of successive chunks of the batch are pipelined inside the call; it is
-        asynchronous with respect to the host when the buffers are page-locked -- synchronise the stream before
-        reading them."""
+        not given).  Copies and kernels of successive chunks of the batch are pipelined inside the call
+        (``chunks`` = 0: chosen from the batch size; 1: no chunking, for callers that already overlap several
+        environments on their own streams); it is asynchronous with respect to the host when the buffers are
+        page-locked -- synchronise the stream before reading them."""
         if actions.dtype != torch.int16 or actions.device.type != "cpu" or actions.numel() != self.n \
                 or not actions.is_contiguous():
             raise ValueError("actions must be a contiguous int16 CPU tensor of shape [num_envs]")
         nw = (self.n + 31) // 32
         if self._host_out is None:
-            self._host_out = (torch.empty(self.n, dtype=torch.float32).pin_memory(),
-                              torch.empty(nw, dtype=torch.int32).pin_memory(),
-                              torch.empty(nw, dtype=torch.int32).pin_memory(),
-                              torch.empty(nw, dtype=torch.int32).pin_memory())
+            self._host_out = self.host_buffers()
+        if self._host_ws is None:
             size = nat.lib().shipenv_step_host_workspace(self.n)
             self._host_ws = torch.empty(size, dtype=torch.uint8, device=self.device)
         outs = [given if given is not None else own
@@ -224,7 +233,7 @@ class BatchedEnvironment:
         flags = nat.F_AUTO_RESET if self.auto_reset else 0
         self.ctx.step_host(self._ships_ptr, self._clock_ptr, actions.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
                            outs[2].data_ptr(), outs[3].data_ptr(), self._host_ws.data_ptr(), self._host_ws.numel(),
-                           self.seed, self.env_id_base, self.n, self.max_steps, flags, self._stream())
+                           self.seed, self.env_id_base, self.n, self.max_steps, flags, int(chunks), self._stream())
         return StepResult(*outs)
 
     def capture_steps(self, actions, **kw):

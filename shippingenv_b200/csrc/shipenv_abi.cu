@@ -76,7 +76,6 @@ struct shipenv_ctx {
   cudaStream_t host_stream[kHostStreams] = {};
   cudaEvent_t host_fork = nullptr, host_join[kHostStreams] = {};
   bool host_ready = false;
-  int host_chunks = kHostStreams;       // SHIPENV_HOST_CHUNKS=1..4 (tuning): chunks per shipenv_step_host call
   std::vector<unsigned char> h_world;
   uint32_t world_bytes = 0;
   bool dirty = true;
@@ -231,7 +230,6 @@ int shipenv_ctx_create(int device, shipenv_ctx** out) {
   if (!c) return fail(SHIPENV_E_ARG, "out of host memory");
   c->device = device;
   { const char* e = getenv("SHIPENV_NO_FAST"); c->no_fast_kernel = e && e[0] == '1'; }
-  { const char* e = getenv("SHIPENV_HOST_CHUNKS"); if (e && e[0] >= '1' && e[0] <= '0' + kHostStreams) c->host_chunks = e[0] - '0'; }
   CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   cudaError_t e = cudaMalloc(&c->d_world, kMaxWorldBytes);
@@ -421,15 +419,15 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
 size_t shipenv_step_host_workspace(int64_t n) {
   if (n <= 0) return 0;
   const size_t nw = (size_t(n) + 31) / 32;
-  // actions (2 B) and rewards (4 B) per env, three mask arrays; every array starts 256-byte aligned
-  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
-  return up(size_t(n) * 2) + up(size_t(n) * 4) + 3 * up(nw * 4);
+  // [actions: 2 B per env, padded to 256 B][rewards: 4 B per env][done | reset | error words]: the results are one
+  // contiguous block, so that a caller whose host buffers are laid out the same way gets them with one copy
+  return ((size_t(n) * 2 + 255) & ~size_t(255)) + size_t(n) * 4 + 3 * nw * 4;
 }
 
 int shipenv_step_host(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* h_actions,
                       float* h_reward, uint32_t* h_done_bits, uint32_t* h_reset_bits, uint32_t* h_error_bits,
                       void* workspace, size_t workspace_bytes, uint64_t seed, uint64_t env_id_base, int64_t n,
-                      int max_steps, uint32_t flags, void* stream_) {
+                      int max_steps, uint32_t flags, int chunks_wanted, void* stream_) {
   if (int rc = check_ctx(c)) return rc;
   if (n < 0 || (n > 0 && (!ships || !clock || !h_actions || !h_reward || !workspace)))
     return fail(SHIPENV_E_ARG, "step_host: null buffer or negative n");
@@ -449,19 +447,20 @@ int shipenv_step_host(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, cons
   }
   if (int rc = sync_world(c, user)) return rc;     // before the fork: every chunk sees the uploaded world
   const size_t nw = (size_t(n) + 31) / 32;
-  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   int16_t* d_act = reinterpret_cast<int16_t*>(ws);
-  float* d_reward = reinterpret_cast<float*>(ws + up(size_t(n) * 2));
+  float* d_reward = reinterpret_cast<float*>(ws + ((size_t(n) * 2 + 255) & ~size_t(255)));
   uint32_t* d_mask[3];
-  d_mask[0] = reinterpret_cast<uint32_t*>(ws + up(size_t(n) * 2) + up(size_t(n) * 4));
-  d_mask[1] = d_mask[0] + up(nw * 4) / 4;
-  d_mask[2] = d_mask[1] + up(nw * 4) / 4;
+  d_mask[0] = reinterpret_cast<uint32_t*>(d_reward + n);
+  d_mask[1] = d_mask[0] + nw;
+  d_mask[2] = d_mask[1] + nw;
   // Chunks of whole 512-env tiles (so mask words, TMA alignment and tile boundaries all fall on chunk boundaries), at
   // least 1 Mi envs each (a copy of less than ~2 MB does not reach PCIe speed).  Chunk 0 runs on the caller's stream,
   // the others on internal streams forked from it and joined back: a one-chunk call involves no other stream.
   constexpr int64_t kGrain = 512, kMinChunk = 1 << 20;
-  int chunks = int(std::min<int64_t>(c->host_chunks, std::max<int64_t>(1, n / kMinChunk)));
+  if (chunks_wanted < 0 || chunks_wanted > kHostStreams) return fail(SHIPENV_E_ARG, "step_host: chunks outside 0..%d", kHostStreams);
+  int chunks = chunks_wanted > 0 ? int(std::min<int64_t>(chunks_wanted, (n + kGrain - 1) / kGrain))
+                                 : int(std::min<int64_t>(kHostStreams, std::max<int64_t>(1, n / kMinChunk)));
   const int64_t per = ((n + chunks - 1) / chunks + kGrain - 1) / kGrain * kGrain;
   chunks = int((n + per - 1) / per);
   if (chunks > 1) CUDA_TRY(cudaEventRecord(c->host_fork, user));
@@ -476,13 +475,30 @@ int shipenv_step_host(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, cons
     if (int rc = step_impl(c, ships + lo, clock + lo, d_act + lo, &io, seed, env_id_base + uint64_t(lo), len, max_steps,
                            flags, 0u, s, 1 + k))
       return rc;
-    CUDA_TRY(cudaMemcpyAsync(h_reward + lo, d_reward + lo, size_t(len) * 4, cudaMemcpyDeviceToHost, s));
+    if (chunks > 1) CUDA_TRY(cudaMemcpyAsync(h_reward + lo, d_reward + lo, size_t(len) * 4, cudaMemcpyDeviceToHost, s));
     if (k > 0) CUDA_TRY(cudaEventRecord(c->host_join[k], s));
   }
   for (int k = 1; k < chunks; ++k) CUDA_TRY(cudaStreamWaitEvent(user, c->host_join[k], 0));
-  uint32_t* h_mask[3] = {h_done_bits, h_reset_bits, h_error_bits};
-  for (int m = 0; m < 3; ++m)
-    if (h_mask[m]) CUDA_TRY(cudaMemcpyAsync(h_mask[m], d_mask[m], nw * 4, cudaMemcpyDeviceToHost, user));
+  // Masks: one copy per run of host arrays that are laid out back to back like the device block (each copy costs
+  // ~10 us of the copy engine whatever its size).  With one chunk the reward copy is still pending and joins the run.
+  struct Span { unsigned char* dst; const unsigned char* src; size_t bytes; };
+  Span spans[4];
+  int n_spans = 0;
+  auto add = [&](void* dst, const void* src, size_t bytes) {
+    if (!dst) return;
+    Span sp{static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), bytes};
+    if (n_spans > 0 && spans[n_spans - 1].dst + spans[n_spans - 1].bytes == sp.dst &&
+        spans[n_spans - 1].src + spans[n_spans - 1].bytes == sp.src)
+      spans[n_spans - 1].bytes += bytes;
+    else
+      spans[n_spans++] = sp;
+  };
+  if (chunks == 1) add(h_reward, d_reward, size_t(n) * 4);
+  add(h_done_bits, d_mask[0], nw * 4);
+  add(h_reset_bits, d_mask[1], nw * 4);
+  add(h_error_bits, d_mask[2], nw * 4);
+  for (int k = 0; k < n_spans; ++k)
+    CUDA_TRY(cudaMemcpyAsync(spans[k].dst, spans[k].src, spans[k].bytes, cudaMemcpyDeviceToHost, user));
   return 0;
 }
 

@@ -434,9 +434,9 @@ def test_cuda_step_host_equals_step(torch_cuda, default_map, n):
         host_acts = acts.pin_memory() if t % 2 == 0 else acts
         if t == 4:      # caller-provided pageable outputs
             outs = (torch.empty(n, dtype=torch.float32), *(torch.empty((n + 31) // 32, dtype=torch.int32) for _ in range(3)))
-            got = envs[1].step_host(host_acts, *outs)
+            got = envs[1].step_host(host_acts, *outs, chunks=3)
         else:
-            got = envs[1].step_host(host_acts)
+            got = envs[1].step_host(host_acts, chunks=t % 2)
         torch.cuda.synchronize()
         assert torch.equal(got.reward, want.reward.cpu()), t
         assert torch.equal(got.done_bits, want.done_bits.cpu()), t
