@@ -28,7 +28,10 @@ gen = torch.Generator(device="cuda").manual_seed(1234)
 acts = [torch.randint(0, 4, (args.envs,), generator=gen, device="cuda", dtype=torch.int16) for _ in range(4)]
 # age the population so that resets, blocked moves and edge rejections occur at their steady rates
 for t in range(300):
-    env.step(acts[t % 4])
+    if args.mode == "policy":
+        env.step_policy()         # the random policy picks cargo up: cargo-loss draws, deliveries, takes at their rates
+    else:
+        env.step(acts[t % 4])
 torch.cuda.synchronize()
 if args.mode == "rollout":
     roots = env.ships[: 1 << 16].contiguous()
