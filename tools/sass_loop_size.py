@@ -30,6 +30,12 @@ for wait in [k for k, (a, t) in enumerate(lines) if "TRYWAIT" in t]:
                 ops[op.split(".")[0]] = ops.get(op.split(".")[0], 0) + 1
             print(f"streaming loop: {k - head + 1} SASS instructions ({lines[head][0]:#x}..{a:#x})")
             print("  " + ", ".join(f"{o} {c}" for o, c in sorted(ops.items(), key=lambda kv: -kv[1])[:14]))
+            alu = sum(c for o, c in ops.items() if o in ("LOP3", "ISETP", "SHF", "PLOP3", "VIADD", "IADD3", "LEA", "SEL", "FSEL",
+                                                         "PRMT", "VIMNMX", "MOV", "IABS", "FSETP", "POPC", "VOTE", "SGXT", "BMSK"))
+            wide = sum("IMAD.WIDE" in t2 or "IMAD.HI" in t2 for _, t2 in body)
+            fma = ops.get("IMAD", 0) - wide
+            print(f"  ALU-pipe ops {alu} (x2 cycles), IMAD {fma} (x2), IMAD.WIDE/HI {wide} (x4): "
+                  f"ALU {2 * alu} / FMA {2 * fma + 4 * wide} / issue {k - head + 1} cycles per tile of a warp")
             found = True
             break
     if found:
