@@ -482,7 +482,7 @@ int shipenv_step_host(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, cons
   // Masks: one copy per run of host arrays that are laid out back to back like the device block (each copy costs
   // ~10 us of the copy engine whatever its size).  With one chunk the reward copy is still pending and joins the run.
   struct Span { unsigned char* dst; const unsigned char* src; size_t bytes; };
-  Span spans[4];
+  Span spans[4] = {};
   int n_spans = 0;
   auto add = [&](void* dst, const void* src, size_t bytes) {
     if (!dst) return;

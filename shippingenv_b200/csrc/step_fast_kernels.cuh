@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   int n_defer = 0;                                   // warp-uniform
   const uint32_t wb = smem_u32(smem);                // world blob
   const uint32_t bits_b = wb + uint32_t(sizeof(WorldHdr));
-  const uint32_t W = uint32_t(w.h->W), H = uint32_t(w.h->H), P = uint32_t(w.h->P);
+  const uint32_t W = uint32_t(w.h->W), H = uint32_t(w.h->H);
   const uint32_t cap = uint32_t(w.h->capacity);
   const uint32_t wpr = uint32_t(w.h->wpr);
   const bool auto_reset = a.flags & SHIPENV_F_AUTO_RESET;
@@ -139,8 +139,6 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
   // lanes 0..2 each own one mask array: one predicated store writes the warp's three ballot words
   uint32_t* const mask_ptr = lane == 0 ? a.io.done_bits : lane == 1 ? a.io.reset_bits : a.io.error_bits;
   const bool mask_lane = lane < 3;
-  const uint32_t reset_rec_y = uint32_t(w.h->cargo0);
-  const uint32_t reset_rec_z = uint32_t(__double2loint(w.h->fuel0)), reset_rec_w = uint32_t(__double2hiint(w.h->fuel0));
   const uint32_t stage_b = smem_u32(stage);
   const uint32_t my_ship = stage_b + uint32_t(tid) * 16u;
   const uint32_t my_clock = stage_b + uint32_t(kTile) * 16u + uint32_t(tid) * 4u;
@@ -215,11 +213,12 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const bool trigger = w_loss <= lds_u32(wb + uint32_t(offsetof(WorldHdr, loss_thr)) + min(uint32_t(rec.y), cap) * 4u);  // :318-320
       const bool arrive = pos1 == (pd & 0xFFFFu);                                         // :325
       const uint32_t c1 = c + 1u;
+      // An episode end with auto-reset (once per few hundred steps of an env) goes the general way too: the reset
+      // draws, the record and clock rewrite and their predicated selects would otherwise ride along on every step.
       const bool do_reset = auto_reset && (no_fuel || (c1 & 0xFFFFu) >= trunc_at);
-      const uint32_t ro = __umulhi(wd[2], P), rd = __umulhi(wd[3], P);                    // :232-233
-      // policy: an off-map choice is re-drawn and a reset needs words 3 and 4 -- both go the general way
+      // policy: an off-map choice is re-drawn -- the general way as well
       const bool general = kPolicy ? (!is_move || !in_map || trigger || arrive || do_reset)
-                                   : (!is_move || (in_map && (trigger || arrive || (do_reset && ro == rd))));
+                                   : (!is_move || (in_map && (trigger || arrive || do_reset)));
       const bool ok = is_move && in_map && !general;
       const bool off_map = !kPolicy && is_move && !in_map;
       const uint32_t ridx = (no_fuel ? 4u : 0u) | ((wbit ^ 1u) << 1) | closer_bit;        // index of move_reward[]
@@ -229,12 +228,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         out.x = (rec.x & 0xFFFF0000u) | pos1;
         out.y = rec.y;
         out.z = uint32_t(__double2loint(fuel1)); out.w = uint32_t(__double2hiint(fuel1));
-        uint32_t c_out = c1;
-        if (do_reset) {                                                                   // :227-243
-          out.x = (lds_u32(wb + uint32_t(offsetof(WorldHdr, port)) + ro * 4u) & 0xFFFFu) | (ro << 16) | (rd << 24);
-          out.y = reset_rec_y; out.z = reset_rec_z; out.w = reset_rec_w;
-          c_out = ((c >> 16) + 1u) << 16;
-        }
+        const uint32_t c_out = c1;
         const float r = lds_f32(wb + uint32_t(offsetof(WorldHdr, move_reward_f32)) + ridx * 4u);
         if (ok) {
           st_stream_u4(a.ships + i, out);
@@ -247,7 +241,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
             if (a.io.reward_f64) a.io.reward_f64[i] = r64;
             if (a.io.status) a.io.status[i] = uint8_t(ok ? SHIPENV_ST_OK : SHIPENV_ST_OFF_MAP);
             if (a.io.taken) a.io.taken[i] = int16_t(kPolicy ? m : act);
-            if (ok) track_episode(a.io, i, r64, do_reset, c);
+            if (ok) track_episode(a.io, i, r64, false, c);
           }
         }
         if (kObs) fin = ok ? out : rec;
@@ -264,7 +258,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         n_defer += __popc(gen_w);
       }
       const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, (ok && no_fuel) || (gflags & kFlagDone));
-      const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, (ok && do_reset) || (gflags & kFlagReset));
+      const uint32_t reset_w = kObs ? __ballot_sync(0xFFFFFFFFu, gflags & kFlagReset) : 0u;   // resets are general-path work
       const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, off_map || (gflags & kFlagError));
       {
         const uint32_t mask_v = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
