@@ -3,20 +3,21 @@
 step_fast_kernel<false,false,1,true> (from the loop head to its backward branch), no GPU needed."""
 import re, subprocess, sys
 lib = sys.argv[1] if len(sys.argv) > 1 else "shippingenv_b200/libshipenv.so"
+ept = sys.argv[2] if len(sys.argv) > 2 else "2"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 fn, lines = None, []
 for l in out.splitlines():
     if "Function :" in l:
         fn = l
         continue
-    if fn and "step_fast_kernelILb0ELb0ELi2ELb1" in fn:
+    if fn and f"step_fast_kernelILb0ELb0ELi{ept}ELb1" in fn:
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
         if m:
             lines.append((int(m.group(1), 16), m.group(2).strip()))
 addr_to_idx = {a: k for k, (a, t) in enumerate(lines)}
 for wait in [k for k, (a, t) in enumerate(lines) if "TRYWAIT" in t]:
     found = False
-    for k in range(wait + 1, min(wait + 900, len(lines))):
+    for k in range(wait + 1, min(wait + 2000, len(lines))):
         a, t = lines[k]
         m = re.search(r"BRA(?:\.U)?\s+(?:\w+,\s*)?0x([0-9a-f]+)", t)
         if m and "DIV" not in t and int(m.group(1), 16) <= lines[wait][0] and int(m.group(1), 16) in addr_to_idx:
