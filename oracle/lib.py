@@ -106,6 +106,14 @@ class Oracle:
                        C.c_int(int(auto_reset)), C.c_uint32(word0))
         return out
 
+    def sample_action(self, ships, clock, seed, env_base=0, word0=0):
+        """Environment.sample_action per env -> (actions int16, words_used uint8, status uint8)."""
+        n = len(ships)
+        a, wu, st = np.zeros(n, np.int16), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        lib().orc_sample_action(C.byref(self.w), _p(ships), _p(clock), _p(a), _p(wu), _p(st), C.c_uint64(seed),
+                                C.c_uint64(env_base), C.c_int64(n), C.c_uint32(word0))
+        return a, wu, st
+
     def observe(self, ships):
         obs = np.zeros((len(ships), 6 + 4 * self.P), np.float32)
         lib().orc_observe(C.byref(self.w), _p(ships), _p(obs), C.c_int64(len(ships)))

@@ -203,3 +203,55 @@ def test_rollouts_and_mcts_on_arbitrary_worlds(seed, W, H, P, density):
     for k in ("action", "root_visits", "child_action", "child_visits"):
         assert (got[k][ok] == ref[k][ok]).all(), k
     assert (got["child_total"][ok].view(np.uint64) == ref["child_total"][ok].view(np.uint64)).all()
+
+
+@settings(max_examples=20, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2**63 - 1), W=st.sampled_from([1, 2, 33, 100, 256]), H=st.sampled_from([1, 31, 100, 256]),
+       P=st.sampled_from([0, 1, 2, 5, 32]), word0=st.sampled_from([0, 1, 3, 6]),
+       base=st.sampled_from([0, (1 << 32) - 2, (1 << 41) + 5]))
+def test_sample_action_and_step_sample_from_arbitrary_states(seed, W, H, P, word0, base):
+    """shipenv_sample_action and shipenv_step_sample (the facade's launches) against the oracle on arbitrary states and
+    worlds: sampled action, words consumed, status; then the step and the look-ahead draw that follows it."""
+    import ctypes
+    import torch
+    from shippingenv_b200 import BatchedEnvironment, _native as nat, unpack_bits
+    rng = np.random.default_rng(seed % (1 << 32))
+    passable, ports, pf, pc = random_world(rng, W, H, P, 0.7)
+    n = 700
+    env = BatchedEnvironment(n, passable=passable, ports=ports, port_fuel=pf, port_cargo=pc, seed=seed, device="cuda:0",
+                             env_id_base=base, auto_reset=False)
+    o = orc.Oracle(passable, ports, pf, pc)
+    ships, clock = world_population(rng, n, W, H, ports)
+    env.load_state(ships, clock)
+    a, wu, stt = (t.cpu().numpy() for t in env.sample_action(word0=word0))
+    ra, rwu, rst = o.sample_action(ships, clock, seed, base, word0)
+    assert (stt == rst).all() and (wu == rwu).all() and (a[rst == 0] == ra[rst == 0]).all()
+    # step_sample: explicit actions (the sampled ones where there is one, junk elsewhere), then the next draw
+    acts = np.where(rst == 0, ra, rng.integers(-3, 270, n)).astype(np.int16)
+    d_act = torch.from_numpy(acts).cuda()
+    dev = env.device
+    nxt = torch.full((n,), -7, dtype=torch.int16, device=dev)
+    nwords = torch.zeros(n, dtype=torch.uint8, device=dev)
+    nstat = torch.zeros(n, dtype=torch.uint8, device=dev)
+    reward64 = torch.zeros(n, dtype=torch.float64, device=dev)
+    status = torch.zeros(n, dtype=torch.uint8, device=dev)
+    io = nat.StepIO()
+    io.reward_f64, io.status = reward64.data_ptr(), status.data_ptr()
+    io.done_bits, io.reset_bits, io.error_bits = env.done_bits.data_ptr(), env.reset_bits.data_ptr(), env.error_bits.data_ptr()
+    env.ctx.step_sample(env.ships.data_ptr(), env.clock.data_ptr(), d_act.data_ptr(), io, nxt.data_ptr(), nwords.data_ptr(),
+                        nstat.data_ptr(), seed, base, n, 0, 0, int(wu.max()) if n else 0, torch.cuda.current_stream().cuda_stream)
+    w0 = int(wu.max())
+    ref = o.step(ships, clock, acts, seed, base, 0, False, w0)
+    g_ships, g_clock = env.state_numpy()
+    assert (g_ships == ships.view(np.uint8).reshape(n, 16)).all() and (g_clock == clock).all()
+    assert (status.cpu().numpy() == ref["status"]).all()
+    assert (reward64.cpu().numpy().view(np.uint64) == ref["reward"].view(np.uint64)).all()
+    assert (unpack_bits(env.done_bits, n).cpu().numpy() == ref["done"].astype(bool)).all()
+    assert (unpack_bits(env.error_bits, n).cpu().numpy() == (ref["status"] != 0)).all()
+    # the look-ahead: word 0 of the new cell after an accepted step, word w0 of the same cell after a rejected one
+    ok = ref["status"] == 0
+    na0, nw0, ns0 = o.sample_action(ships, clock, seed, base, 0)
+    na1, nw1, ns1 = o.sample_action(ships, clock, seed, base, w0)
+    want_a, want_w, want_s = np.where(ok, na0, na1), np.where(ok, nw0, nw1), np.where(ok, ns0, ns1)
+    assert (nstat.cpu().numpy() == want_s).all() and (nwords.cpu().numpy() == want_w).all()
+    assert (nxt.cpu().numpy()[want_s == 0] == want_a[want_s == 0]).all()
