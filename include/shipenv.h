@@ -12,7 +12,11 @@
  *     the caller (torch tensors: tensor.data_ptr()); the library allocates nothing per
  *     call.  Arguments of shipenv_set_* are HOST pointers (tiny tables, copied);
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
- *     all work is enqueued on it, nothing synchronises;
+ *     all work is enqueued on it (shipenv_step_host also uses internal streams, forked from and
+ *     joined to it); nothing blocks the host except shipenv_stream_synchronize;
+ *   - two entry points serve callers whose data lives in HOST memory, as the reference's does:
+ *     shipenv_step_host (batched: host actions in, host rewards / masks out) and the N = 1 pair
+ *     shipenv_host_device_pointer / shipenv_step_sample (the facade's page-locked ship block);
  *   - a context belongs to one device; calls on one context must not race.
  *
  * Batched contract ("Batched contract"):
