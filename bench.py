@@ -428,7 +428,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "shipenv::step_fast_kernel",
-                         "algorithmic_bytes_per_launch": n * BYTES_PER_STEP},
+                         "algorithmic_bytes_per_launch": n * BYTES_PER_STEP,
+                         "launch_us": kernel_ms * 1e3,
+                         "how": "elapsed / K over the timed region; launches of independent env groups sit on "
+                                "different streams and overlap at their boundaries",
+                         "frac_one_stream": n * BYTES_PER_STEP / (one_stream_ms / K * 1e-3) / 1e9 / peak},
             "e2e": {"value": n_total * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n + 12 * nw, "steps": Ke,
                     "what": "shipenv_step_host (BatchedEnvironment.step_host): the C-ABI call takes int16 actions from "
