@@ -216,9 +216,13 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       // An episode end with auto-reset (once per few hundred steps of an env) goes the general way too: the reset
       // draws, the record and clock rewrite and their predicated selects would otherwise ride along on every step.
       const bool do_reset = auto_reset && (no_fuel || (c1 & 0xFFFFu) >= trunc_at);
+      // (the fused-observation variant resolves general lanes on the spot, a whole warp waiting for them, so it keeps
+      // the reset in line: words 2 and 3 are the two port draws, :232-233; equal draws need more words)
+      const uint32_t ro = kObs ? __umulhi(wd[2], uint32_t(w.h->P)) : 0u, rd = kObs ? __umulhi(wd[3], uint32_t(w.h->P)) : 0u;
+      const bool reset_general = (kObs && !kPolicy) ? (do_reset && ro == rd) : do_reset;
       // policy: an off-map choice is re-drawn -- the general way as well
       const bool general = kPolicy ? (!is_move || !in_map || trigger || arrive || do_reset)
-                                   : (!is_move || (in_map && (trigger || arrive || do_reset)));
+                                   : (!is_move || (in_map && (trigger || arrive || reset_general)));
       const bool ok = is_move && in_map && !general;
       const bool off_map = !kPolicy && is_move && !in_map;
       const uint32_t ridx = (no_fuel ? 4u : 0u) | ((wbit ^ 1u) << 1) | closer_bit;        // index of move_reward[]
@@ -228,7 +232,13 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         out.x = (rec.x & 0xFFFF0000u) | pos1;
         out.y = rec.y;
         out.z = uint32_t(__double2loint(fuel1)); out.w = uint32_t(__double2hiint(fuel1));
-        const uint32_t c_out = c1;
+        uint32_t c_out = c1;
+        if (kObs && !kPolicy && do_reset) {                                                // :227-243
+          out.x = (lds_u32(wb + uint32_t(offsetof(WorldHdr, port)) + ro * 4u) & 0xFFFFu) | (ro << 16) | (rd << 24);
+          out.y = uint32_t(w.h->cargo0);
+          out.z = uint32_t(__double2loint(w.h->fuel0)); out.w = uint32_t(__double2hiint(w.h->fuel0));
+          c_out = ((c >> 16) + 1u) << 16;
+        }
         const float r = lds_f32(wb + uint32_t(offsetof(WorldHdr, move_reward_f32)) + ridx * 4u);
         if (ok) {
           st_stream_u4(a.ships + i, out);
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
             if (a.io.reward_f64) a.io.reward_f64[i] = r64;
             if (a.io.status) a.io.status[i] = uint8_t(ok ? SHIPENV_ST_OK : SHIPENV_ST_OFF_MAP);
             if (a.io.taken) a.io.taken[i] = int16_t(kPolicy ? m : act);
-            if (ok) track_episode(a.io, i, r64, false, c);
+            if (ok) track_episode(a.io, i, r64, kObs && !kPolicy && do_reset, c);
           }
         }
         if (kObs) fin = ok ? out : rec;
@@ -258,7 +268,8 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         n_defer += __popc(gen_w);
       }
       const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, (ok && no_fuel) || (gflags & kFlagDone));
-      const uint32_t reset_w = kObs ? __ballot_sync(0xFFFFFFFFu, gflags & kFlagReset) : 0u;   // resets are general-path work
+      const uint32_t reset_w = kObs ? __ballot_sync(0xFFFFFFFFu, (!kPolicy && ok && do_reset) || (gflags & kFlagReset))
+                                    : 0u;                          // without observations resets are general-path work
       const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, off_map || (gflags & kFlagError));
       {
         const uint32_t mask_v = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
