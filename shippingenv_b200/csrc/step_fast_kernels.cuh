@@ -10,7 +10,7 @@ namespace shipenv {
 //
 // Same TMA producer / consumer pipeline as step_kernel, but the streaming loop contains the
 // straight-line MOVE case only.  Lanes that need anything else (non-move action, cargo-loss
-// draw, arrival, destination re-draw, unset destination) push their env index on a per-warp
+// draw, arrival, episode end with auto-reset, unset destination) push their env index on a per-warp
 // shared-memory list; the warp drains the list through step_general OUTSIDE the streaming
 // loop, 32 deferred envs per call, and ORs their done/reset/error bits into the mask words.
 // ------------------------------------------------------------------------------------------
