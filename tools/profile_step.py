@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """A short run of the bench workload (2,097,152 envs, random moves, auto-reset) for ncu.
 
-    python tools/profile_step.py [--envs N] [--steps K] [--mode moves|policy|obs|rollout]
+    python tools/profile_step.py [--envs N] [--steps K] [--mode moves|policy|obs|rollout|mcts]
 """
 import argparse
 import os
@@ -33,7 +33,11 @@ for t in range(300):
     else:
         env.step(acts[t % 4])
 torch.cuda.synchronize()
-if args.mode == "rollout":
+if args.mode == "mcts":
+    roots = env.ships[: 1 << 16].contiguous()
+    for t in range(args.steps):
+        env.mcts(50, 100, roots=roots)
+elif args.mode == "rollout":
     roots = env.ships[: 1 << 16].contiguous()
     for t in range(args.steps):
         env.rollout(50, 100, roots=roots)
