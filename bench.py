@@ -17,6 +17,7 @@ is pure Python and cannot travel to the GPU box) on all host cores on the same w
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -33,6 +34,7 @@ GROUPS = 4                   # env groups per GPU, stepped round-robin (working 
 ACTION_POOL = 32             # distinct pre-generated action vectors, cycled
 FLUSH_BYTES = 256 << 20      # > 126 MB L2
 METRIC = "env-steps/sec (whole box)"
+CHAINED_ONE_STREAM = False
 
 
 def world():
@@ -212,14 +214,75 @@ def workload_config(gpus):
                         "device), auto-reset on done or 1000 steps, Philox seed 0x5EED",
             "envs_per_launch": ENVS_PER_GPU, "env_groups_per_gpu": GROUPS, "max_steps": MAX_STEPS,
             "l2": "inputs larger than L2: 4 env groups of 2,097,152 envs per GPU stepped round-robin (216 MB working "
-                  "set vs 126 MB L2); group g launches on stream g; timed from one start event to the latest of "
-                  "the per-stream end events",
+                  "set vs 126 MB L2); group g launches on stream g (forked from / joined to the timing stream)",
             "bytes_per_env_step": BYTES_PER_STEP}
 
 
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+def timed_regions(torch, dev, issue, K, min_total_ms=50.0, max_reps=400, barrier=None):
+    """Time the K-launch region `issue()` enqueues (a CUDA-graph replay, or K eager launches) until at least
+    `min_total_ms` of device time has been measured; one CUDA-event pair per region on the current stream.
+    Returns the list of region times in ms."""
+    issue()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); issue(); e1.record()
+    torch.cuda.synchronize(dev)
+    est = max(e0.elapsed_time(e1), 1e-3)
+    reps = int(min(max_reps, max(5, math.ceil(min_total_ms / est))))
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+    if barrier:
+        barrier()
+    for r in range(reps):
+        starts[r].record()
+        issue()
+        stops[r].record()
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize(dev)
+    return [s.elapsed_time(e) for s, e in zip(starts, stops)]
+
+
+def copy_link_rates(torch, dev, n, G, iters=24):
+    """Pinned-memory copy rates of this rank's host link with the e2e leg's own transfer sizes: G streams, each
+    alternating one host-to-device copy of 2n bytes and one device-to-host copy of 4n + 12 ceil(n/32) bytes."""
+    nw = (n + 31) // 32
+    h_in = [torch.empty(2 * n, dtype=torch.uint8).pin_memory() for _ in range(G)]
+    h_out = [torch.empty(4 * n + 12 * nw, dtype=torch.uint8).pin_memory() for _ in range(G)]
+    d_in = [torch.empty(2 * n, dtype=torch.uint8, device=dev) for _ in range(G)]
+    d_out = [torch.empty(4 * n + 12 * nw, dtype=torch.uint8, device=dev) for _ in range(G)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
+    out = {}
+    for mode in ("h2d", "d2h", "both"):
+        torch.cuda.synchronize(dev)
+        t0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+        t0.record()
+        for g, st in enumerate(streams):
+            st.wait_event(t0)
+            with torch.cuda.stream(st):
+                for _ in range(iters):
+                    if mode != "d2h":
+                        d_in[g].copy_(h_in[g], non_blocking=True)
+                    if mode != "h2d":
+                        h_out[g].copy_(d_out[g], non_blocking=True)
+                ends[g].record(st)
+        torch.cuda.synchronize(dev)
+        ms = max(t0.elapsed_time(e) for e in ends)
+        nbytes = G * iters * ((2 * n if mode != "d2h" else 0) + (4 * n + 12 * nw if mode != "h2d" else 0))
+        out[mode] = nbytes / (ms * 1e-3) / 1e9
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -246,70 +309,101 @@ def run_ours(args):
 
     n = args.envs
     G = args.groups
+    K, W = args.steps, args.warmup
     # G independent env groups per GPU, stepped round-robin: one launch touches 46 B x n = 96 MB and the
     # next G-1 launches stream 3 x 96 MB through the 126 MB L2 before the group comes round again, so
     # every timed launch reads its inputs from HBM ("inputs larger than L2").
     envs = [BatchedEnvironment(n, passable=world(), seed=SEED, device=dev, env_id_base=(rank * G + g) * n,
                                max_steps=MAX_STEPS, auto_reset=True) for g in range(G)]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    block = torch.randint(0, 4, (ACTION_POOL, n), generator=gen, device=dev, dtype=torch.int16)
+    pool = [block[k] for k in range(ACTION_POOL)]
+    # Steady state before anything is timed (untimed, independent of --warmup): every group is aged with the fused
+    # T-step kernel so that ships have diffused, fuel runs out at its steady rate (an episode lasts ~280 steps), the
+    # deferred auto-resets and the off-map rejections are in the timed mix.
     for e in envs:
         e.reset()
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = [torch.randint(0, 4, (n,), generator=gen, device=dev, dtype=torch.int16) for _ in range(ACTION_POOL)]
-    K, W = args.steps, args.warmup
+        for _ in range(max(0, args.age) // ACTION_POOL):
+            e.step_many(block, want_masks=False)
 
     def barrier():
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident: K launches, group g on stream g, between CUDA events ----
+    # ---- device-resident: K launches, group g on stream g ----
     # The groups are independent, so each gets its own stream: the tail of one group's launch overlaps the head
     # of the next group's (within a group, consecutive launches still serialise -- and overlap their prologue
-    # through programmatic dependent launch).  Timed on the device: one start event that every stream waits on,
-    # one end event per stream, duration = start -> latest end.
+    # through programmatic dependent launch).  The K-launch region is captured ONCE in a CUDA graph (fork from the
+    # capture stream to the group streams, join back), so that a timed region costs the host one graph launch and
+    # host scheduling noise cannot reach the device timeline; the region is replayed until >= 50 ms have been timed
+    # and the MEDIAN region time is reported (min / max alongside).
     gstreams = [torch.cuda.Stream(device=dev) for _ in range(G)]
 
-    def run_steps(count):
+    def issue_steps(count, chained=False):
         for t in range(count):
-            envs[t % G].step(pool[t % ACTION_POOL])       # env g launches on its own stream (use_stream below)
+            envs[t % G].step(pool[t % ACTION_POOL], chained=chained)
+
+    def capture(multi_stream, chained=False):
+        for g in range(G):
+            envs[g].use_stream(gstreams[g] if multi_stream else None)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            cur = torch.cuda.current_stream(dev)
+            if multi_stream:
+                for st in gstreams:
+                    st.wait_stream(cur)
+            issue_steps(K, chained)
+            if multi_stream:
+                for st in gstreams:
+                    cur.wait_stream(st)
+        for g in range(G):
+            envs[g].use_stream(None)
+        return graph
 
     for g, st in enumerate(gstreams):
         st.wait_stream(torch.cuda.current_stream(dev))
-        envs[g].use_stream(st)
-    run_steps(W)
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    g_end = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
-    barrier()
+    issue_steps(W)                                    # W untimed warm-up steps (eager, current stream)
+    torch.cuda.synchronize(dev)
+    how_issue = "cuda_graph"
     launches0 = launch_count()
+    try:
+        graph_multi = capture(True)
+        issue_multi = graph_multi.replay
+    except Exception as exc:                           # capture not possible: eager launches, host cost reported
+        how_issue = f"eager ({type(exc).__name__})"
+
+        def issue_multi():
+            cur = torch.cuda.current_stream(dev)
+            for g, st in enumerate(gstreams):
+                st.wait_stream(cur)
+                envs[g].use_stream(st)
+            issue_steps(K)
+            for g, st in enumerate(gstreams):
+                cur.wait_stream(st)
+                envs[g].use_stream(None)
+    launches_per_region = launch_count() - launches0 if how_issue == "cuda_graph" else K
     with ClockSampler(local) as clocks:
-        e0.record()
-        for st in gstreams:
-            st.wait_event(e0)
         t_host = time.perf_counter()
-        run_steps(K)
-        host_us = (time.perf_counter() - t_host) / K * 1e6     # host cost of one launch (must stay below the GPU time)
-        for g, st in enumerate(gstreams):
-            g_end[g].record(st)
-        barrier()
-    launches = launch_count() - launches0
-    total_ms = max(e0.elapsed_time(e) for e in g_end)
+        region_ms = timed_regions(torch, dev, issue_multi, K, barrier=barrier)
+        host_wall_s = time.perf_counter() - t_host
+    total_ms = median(region_ms)
     err = int(sum(int(e.error_bits.ne(0).sum().item()) for e in envs))
+    resets = int(sum(int(unpack_bits(e.reset_bits, n).sum().item()) for e in envs))
 
-    # ---- the same K launches on ONE stream (strictly back to back), reported separately ----
-    for e in envs:
-        e.use_stream(None)
-    barrier()
-    e0.record()
-    for t in range(K):
-        envs[t % G].step(pool[t % ACTION_POOL])
-    e1.record()
-    barrier()
-    one_stream_ms = e0.elapsed_time(e1)
+    # ---- the same K launches on ONE stream (strictly in stream order), reported separately ----
+    try:
+        graph_one = capture(False, chained=args.chained)
+        issue_one = graph_one.replay
+    except Exception:
+        def issue_one():
+            issue_steps(K, args.chained)
+    one_ms = median(timed_regions(torch, dev, issue_one, K, barrier=barrier))
 
-    # ---- single group, L2 flushed by a 256 MiB fill between steps, one event pair per step (reported separately) ----
+    # ---- single group, L2 flushed by a 256 MiB fill between steps, one event pair per step: the isolated launch ----
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    Kf = min(K, 256)
+    Kf = max(16, min(K, 128))
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
     barrier()
@@ -319,7 +413,7 @@ def run_ours(args):
         envs[0].step(pool[t % ACTION_POOL])
         stops[t].record()
     barrier()
-    flushed_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops)) * K / Kf
+    isolated_ms = median([s.elapsed_time(e) for s, e in zip(starts, stops)])
     del flush
 
     # ---- end to end: actions from pinned host memory, reward + masks back to pinned host memory ----
@@ -336,74 +430,59 @@ def run_ours(args):
         with torch.cuda.stream(streams[g]):
             envs[g].step_host(h_act[g], *h_out[g], chunks=1)   # the groups already overlap each other
 
-    for t in range(2 * G):
-        e2e_step(t)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
-    t0.record()                                  # on the current stream; the group streams wait for it
-    for st in streams:
-        st.wait_event(t0)
-    for t in range(Ke):
-        e2e_step(t)
-    for g, st in enumerate(streams):
-        ends[g].record(st)
-    barrier()
-    e2e_ms = max(t0.elapsed_time(e) for e in ends)
+    def e2e_region():
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cur)
+        for t in range(Ke):
+            e2e_step(t)
+        for st in streams:
+            cur.wait_stream(st)
+
+    e2e_ms = median(timed_regions(torch, dev, e2e_region, Ke, min_total_ms=200.0, max_reps=40, barrier=barrier))
     checksum = float(sum(float(h.sum()) for h in h_reward))
+    link = copy_link_rates(torch, dev, n, G)
+    if world_size > 1:                                       # the ranks share the host: rates with all of them copying
+        dist.barrier()
+        link_all = copy_link_rates(torch, dev, n, G)
+        dist.barrier()
+    else:
+        link_all = link
+
+    # ---- episode statistics: the one collective of the path (NCCL all-reduce of 6 doubles), checked against a gather
+    stats_check = None
+    if world_size > 1:
+        from shippingenv_b200.stats import reduce_stats, summarize
+        tracked = BatchedEnvironment(1 << 16, passable=world(), seed=SEED, device=dev, env_id_base=rank << 16,
+                                     max_steps=40, auto_reset=True, track_stats=True)
+        tracked.reset()
+        for t in range(64):
+            tracked.step(pool[t % ACTION_POOL][:1 << 16].contiguous())
+        summary = tracked.episode_summary()                 # all-reduce over NCCL
+        every = [torch.zeros_like(tracked.stats) for _ in range(world_size)]
+        dist.all_gather(every, tracked.stats)               # the same numbers gathered rank by rank
+        st = torch.stack(every).cpu().numpy()
+        want = dict(episodes=float(st[:, 3].sum()), sum_return=float(st[:, 0].sum()), best=float(st[:, 4].max()),
+                    worst=float(st[:, 5].min()))
+        red = reduce_stats(tracked.stats).cpu().numpy()
+        stats_check = {"episodes": summary["total_episodes"], "mean_return": summary["mean_return"],
+                       "nccl_equals_gathered": bool(red[3] == want["episodes"] and red[4] == want["best"]
+                                                    and red[5] == want["worst"]
+                                                    and abs(red[0] - want["sum_return"]) <= 1e-9 * abs(want["sum_return"]))}
 
     # ---- the other device paths of the scope table, N = 1 only, a few launches each (reported as extras) ----
     extras = {}
     if world_size == 1 and not args.no_extras:
-        def timed(fn, reps):
-            fn()
-            torch.cuda.synchronize(dev)
-            e0.record()
-            for _ in range(reps):
-                fn()
-            e1.record()
-            torch.cuda.synchronize(dev)
-            return e0.elapsed_time(e1) / reps
-        g0 = envs[0]
-        ms = timed(lambda: g0.step_policy(), 50)
-        extras["policy_step"] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_launch": ms,
-                                 "what": "action -1: on-device sample_action + retry (Environment.sample_action loop)"}
-        ms = timed(lambda: g0.step(pool[0], want_obs=True), 50)
-        extras["step_with_observation"] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_launch": ms,
-                                           "bytes_per_env_step": 150, "hbm_gbs": n * 150 / (ms * 1e-3) / 1e9,
-                                           "what": "fused preprocess_state rows, f32 [n, 26], TMA bulk stores"}
-        ms = timed(lambda: g0.valid_action_bits(), 50)
-        extras["valid_action_mask"] = {"envs_per_s": n / (ms * 1e-3), "ms_per_launch": ms}
-        # BASELINE configs[1]: 4,096 envs -- launch-bound; eager launches vs one CUDA-graph replay of 256 steps
-        small = BatchedEnvironment(4096, passable=world(), seed=SEED, device=dev, max_steps=MAX_STEPS)
-        small.reset()
-        sact = torch.randint(0, 4, (256, 4096), generator=gen, device=dev, dtype=torch.int16)
-        ms = timed(lambda: [small.step(sact[t]) for t in range(256)], 3)
-        graph = small.capture_steps(sact)
-        msg = timed(lambda: graph.replay(), 10)
-        extras["config_4096_envs"] = {"eager_env_steps_per_s": 4096 * 256 / (ms * 1e-3),
-                                      "cuda_graph_env_steps_per_s": 4096 * 256 / (msg * 1e-3),
-                                      "us_per_step_eager": ms * 1e3 / 256, "us_per_step_graph": msg * 1e3 / 256,
-                                      "what": "BASELINE configs[1]: 4,096 envs on one GPU, random moves, auto-reset"}
-        R, S, L = 65536, 50, 100                      # BASELINE configs[3]
-        roots = g0.ships[:R].contiguous()
-        holder = {}
-        ms = timed(lambda: holder.update(out=g0.rollout(S, L, roots=roots)), 5)
-        rsteps = int(holder["out"]["steps"].sum().item())
-        extras["mcts_rollouts"] = {"roots": R, "simulations": S, "max_rollout_steps": L, "ms_per_launch": ms,
-                                   "rollout_steps_per_s": rsteps / (ms * 1e-3), "roots_per_s": R / (ms * 1e-3),
-                                   "what": "MCTSAgent._rollout x 50 per root in one kernel (reference: 5.6 roots/s/core)"}
-        ms = timed(lambda: g0.mcts(S, L, roots=roots), 2)
-        extras["mcts_choose_action"] = {"roots": R, "simulations": S, "max_rollout_steps": L, "ms_per_launch": ms,
-                                        "decisions_per_s": R / (ms * 1e-3),
-                                        "what": "MCTSAgent.choose_action (UCB1 tree + expansion + rollouts + backprop) per "
-                                                "root in one kernel; reference: 0.18 s per decision per core"}
+        extras = run_extras(torch, dev, envs[0], pool, block, gen, n)
 
     # ---- max over ranks ----
-    times = torch.tensor([total_ms, flushed_ms, e2e_ms, one_stream_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([total_ms, isolated_ms, e2e_ms, one_ms, min(region_ms), max(region_ms)], dtype=torch.float64,
+                         device=dev)
+    rates = torch.tensor([link_all["h2d"], link_all["d2h"], link_all["both"]], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, flushed_ms, e2e_ms, one_stream_ms = times.tolist()
+        dist.all_reduce(rates, op=dist.ReduceOp.SUM)
+    total_ms, isolated_ms, e2e_ms, one_ms, region_min, region_max = times.tolist()
 
     if rank == 0:
         n_total = n * world_size
@@ -414,34 +493,64 @@ def run_ours(args):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = n * BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+        algo = n * BYTES_PER_STEP
+        achieved = algo / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        prof = os.path.join(ROOT, "profiles", "r2_step_kernel_traffic.json")
         if os.path.exists(prof):
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            traffic, traffic_src = pj.get("dram_bytes_per_launch"), pj.get("how")
+        e2e_bytes = 2 * n + 4 * n + 12 * nw
+        e2e_value = n_total * Ke / (e2e_ms * 1e-3)
+        link_total = rates.tolist()
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world_size, "steps": K,
             "warmup": W, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world_size),
-            "value_one_stream": n_total * K / (one_stream_ms * 1e-3),
-            "value_l2_flushed_per_step_events": n_total * K / (flushed_ms * 1e-3),
+            "timing": {"how": f"{how_issue}: the K-step region (group g on stream g, forked from and joined to one stream) "
+                              "is issued as one unit and timed with one CUDA-event pair; repeated until >= 50 ms were "
+                              "timed; ms_per_step = median region time / K, max over ranks",
+                       "regions": len(region_ms), "region_ms_median": total_ms, "region_ms_min": region_min,
+                       "region_ms_max": region_max, "host_wall_s": host_wall_s,
+                       "population": f"every group aged {args.age} steps (untimed) before the warm-up: "
+                                     f"{resets} auto-resets and {err} mask words with rejected (off-map) actions in the "
+                                     f"last timed step of the {G} groups"},
+            "value_one_stream": n_total * K / (one_ms * 1e-3),
+            "value_isolated_launch_l2_flushed": n_total / (isolated_ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "shipenv::step_fast_kernel",
-                         "algorithmic_bytes_per_launch": n * BYTES_PER_STEP,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
+                         "kernel": "shipenv::step_fast_kernel<false,false,2,true>",
+                         "algorithmic_bytes_per_launch": algo,
                          "launch_us": kernel_ms * 1e3,
-                         "how": "elapsed / K over the timed region; launches of independent env groups sit on "
-                                "different streams and overlap at their boundaries",
-                         "frac_one_stream": n * BYTES_PER_STEP / (one_stream_ms / K * 1e-3) / 1e9 / peak},
-            "e2e": {"value": n_total * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                         "how": "algorithmic bytes / (median region time / K); launches of independent env groups sit "
+                                "on different streams and overlap at their boundaries",
+                         "frac_one_stream": algo / (one_ms / K * 1e-3) / 1e9 / peak,
+                         "one_stream_how": "the same K launches in one stream, groups round-robin"
+                                           + (", SHIPENV_F_CHAINED (pre-generated actions)" if args.chained else ""),
+                         "frac_isolated": algo / (isolated_ms * 1e-3) / 1e9 / peak,
+                         "isolated_how": "one launch alone between CUDA events, L2 flushed by a 256 MiB fill before it "
+                                         "(median of per-launch times): ramp and tail fully exposed"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s",
                     "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n + 12 * nw, "steps": Ke,
                     "what": "shipenv_step_host (BatchedEnvironment.step_host): the C-ABI call takes int16 actions from "
                             "page-locked host memory and delivers f32 reward + done/reset/error masks to page-locked "
                             "host memory; env groups round-robin on one stream each, so the copies of one group overlap the "
-                            "kernel of another (chunks=1; a lone batch would let the call pipeline 1 Mi-env chunks)"},
-            "gpu_launches": launches, "host_us_per_launch": host_us, "clocks": clocks.summary(), "cpus_pinned_to_gpu_numa_node": numa,
-            "rejected_actions_last_step": err, "reward_checksum": checksum,
+                            "kernel of another (chunks=1; a lone batch would let the call pipeline 1 Mi-env chunks)",
+                    "roofline": {"bound": "host link (pinned-memory copies)", "unit": "GB/s",
+                                 "achieved": e2e_value * e2e_bytes / n / 1e9,
+                                 "peak": link_total[2],
+                                 "frac": (e2e_value * e2e_bytes / n / 1e9) / link_total[2] if link_total[2] else None,
+                                 "peak_how": "measured in this run: all ranks at once copy the e2e leg's own transfer "
+                                             "sizes in both directions on the same number of streams, no kernels",
+                                 "h2d_only_gbs": link_total[0], "d2h_only_gbs": link_total[1],
+                                 "rank0_alone_both_gbs": link["both"]}},
+            "gpu_launches": launches_per_region, "timed_regions": len(region_ms),
+            "clocks": clocks.summary(), "cpus_pinned_to_gpu_numa_node": numa,
+            "rejected_actions_last_step": err, "auto_resets_last_step": resets, "reward_checksum": checksum,
         }
+        if stats_check:
+            line["episode_stats_nccl"] = stats_check
         if extras:
             line["extras"] = extras
         if world_size == 1 and not args.no_cpu:
@@ -472,6 +581,98 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_extras(torch, dev, g0, pool, block, gen, n):
+    """The other device paths of SURVEY 8 on one GPU, a few launches each."""
+    import importlib.util
+    from shippingenv_b200 import BatchedEnvironment
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    extras = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    ms = timed(lambda: g0.step_policy(), 50)
+    extras["policy_step"] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_launch": ms,
+                             "what": "action -1: on-device sample_action + retry (Environment.sample_action loop)"}
+    ms = timed(lambda: g0.step(pool[0], want_obs=True), 50)
+    extras["step_with_observation"] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_launch": ms,
+                                       "bytes_per_env_step": 150, "hbm_gbs": n * 150 / (ms * 1e-3) / 1e9,
+                                       "what": "fused preprocess_state rows, f32 [n, 26], TMA bulk stores"}
+    ms = timed(lambda: g0.valid_action_bits(), 50)
+    extras["valid_action_mask"] = {"envs_per_s": n / (ms * 1e-3), "ms_per_launch": ms}
+    # the fused T-step entry point on the headline batch: 6 + 40/T bytes per env-step, bound by instruction issue
+    T = block.shape[0]
+    ms = timed(lambda: g0.step_many(block), 5)
+    extras["step_many_2Mi_envs"] = {
+        "env_steps_per_s": n * T / (ms * 1e-3), "ms_per_launch": ms, "steps_per_launch": T,
+        "roofline": {"bound": "issue", "algorithmic_bytes_per_env_step": 6 + 40 / T,
+                     "hbm_gbs": n * T * (6 + 40 / T) / (ms * 1e-3) / 1e9},
+        "what": "shipenv_step_many: T steps per launch, ship record and clock in registers; never part of the 46 B headline"}
+    # BASELINE configs[1]: 4,096 envs -- one launch per step is launch-bound; eager vs CUDA graph vs shipenv_step_many
+    small = BatchedEnvironment(4096, passable=world(), seed=SEED, device=dev, max_steps=MAX_STEPS)
+    small.reset()
+    sact = torch.randint(0, 4, (256, 4096), generator=gen, device=dev, dtype=torch.int16)
+    ms = timed(lambda: [small.step(sact[t]) for t in range(256)], 3)
+    graph = small.capture_steps(sact)
+    msg = timed(lambda: graph.replay(), 10)
+    msm = timed(lambda: small.step_many(sact), 20)
+    extras["config_4096_envs"] = {"eager_env_steps_per_s": 4096 * 256 / (ms * 1e-3),
+                                  "cuda_graph_env_steps_per_s": 4096 * 256 / (msg * 1e-3),
+                                  "step_many_env_steps_per_s": 4096 * 256 / (msm * 1e-3),
+                                  "us_per_step_eager": ms * 1e3 / 256, "us_per_step_graph": msg * 1e3 / 256,
+                                  "us_per_step_step_many": msm * 1e3 / 256,
+                                  "what": "BASELINE configs[1]: 4,096 envs on one GPU, random moves, auto-reset; 256 steps as "
+                                          "256 launches, as one graph replay, and as one shipenv_step_many launch"}
+    # BASELINE configs[3] (SURVEY 8d): roots = env ids 0..R-1 after reset, advanced by 10 random legal moves
+    R, S, L = 65536, 50, 100
+    rootenv = BatchedEnvironment(R, passable=world(), seed=SEED, device=dev, env_id_base=0, auto_reset=False)
+    rootenv.reset()
+    rgen = torch.Generator(device=dev).manual_seed(4321)
+    rejected = 0
+    for _ in range(10):
+        r = rootenv.step(torch.randint(0, 4, (R,), generator=rgen, device=dev, dtype=torch.int16))
+        rejected += int(r.error_bits.ne(0).sum().item())
+    roots = rootenv.ships.clone()
+    holder = {}
+    ms = timed(lambda: holder.update(out=rootenv.rollout(S, L, roots=roots)), 5)
+    rsteps = int(holder["out"]["steps"].sum().item())
+    extras["mcts_rollouts"] = {"roots": R, "simulations": S, "max_rollout_steps": L, "ms_per_launch": ms,
+                               "rollout_steps_per_s": rsteps / (ms * 1e-3), "roots_per_s": R / (ms * 1e-3),
+                               "roots_how": f"fresh reset of env ids 0..{R - 1}, then 10 uniform random N/E/S/W moves "
+                                            f"({rejected} mask words with rejected moves)",
+                               "what": "MCTSAgent._rollout x 50 per root in one kernel (reference: 5.6 roots/s/core)"}
+    ms = timed(lambda: rootenv.mcts(S, L, roots=roots), 3)
+    extras["mcts_choose_action"] = {"roots": R, "simulations": S, "max_rollout_steps": L, "ms_per_launch": ms,
+                                    "decisions_per_s": R / (ms * 1e-3),
+                                    "what": "MCTSAgent.choose_action (UCB1 tree + expansion + rollouts + backprop) per "
+                                            "root in one kernel; reference: 0.18 s per decision per core"}
+    # BASELINE configs[4]: the reference's DQN loop with env + observation + valid-action mask on the device
+    try:
+        spec = importlib.util.spec_from_file_location("dqn_device", os.path.join(ROOT, "examples", "dqn_device.py"))
+        dqn = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(dqn)
+        runs = {}
+        for name, envs_, steps_, graph_ in (("1_env_eager", 1, 300, False), ("1_env_cuda_graph", 1, 1500, True),
+                                            ("4096_envs_eager", 4096, 100, False), ("4096_envs_cuda_graph", 4096, 300, True)):
+            out = dqn.train(envs=envs_, steps=steps_, graph=graph_, device=str(dev))
+            runs[name] = {"agent_steps_per_s": out["agent_steps_per_s"], "iterations_per_s": out["iterations_per_s"],
+                          "cuda_graph": out["cuda_graph"]}
+        extras["dqn_loop"] = dict(runs, what="BASELINE configs[4] (examples/dqn_device.py): reference hyper-parameters "
+                                             "(batch 32, memory 2000, MLP 26-128-128-259), env step + fused observation + "
+                                             "valid-action mask on the device feeding a stock torch Q-network and Adam; "
+                                             "the reference runs ~220 agent steps/s on CPU")
+    except Exception as exc:                          # an example failing must not take the headline down
+        extras["dqn_loop"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return extras
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -480,6 +681,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per launch")
     ap.add_argument("--groups", type=int, default=GROUPS, help="env groups per GPU")
+    ap.add_argument("--age", type=int, default=1536, help="untimed steps every env group is aged by before timing")
+    ap.add_argument("--chained", action="store_true", default=CHAINED_ONE_STREAM,
+                    help="one-stream leg: SHIPENV_F_CHAINED launches")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

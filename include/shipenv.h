@@ -17,7 +17,10 @@
  *   - two entry points serve callers whose data lives in HOST memory, as the reference's does:
  *     shipenv_step_host (batched: host actions in, host rewards / masks out) and the N = 1 pair
  *     shipenv_host_device_pointer / shipenv_step_sample (the facade's page-locked ship block);
- *   - a context belongs to one device; calls on one context must not race.
+ *   - a context belongs to one device; calls on one context must not race (one host thread at a time).  Launches
+ *     of one context may be in flight on several streams at once: the library orders its own world upload before
+ *     them and gives each launch its own scheduling state.  Two launches that touch the same ships are the
+ *     caller's to order, as with any kernel.
  *
  * Batched contract ("Batched contract"):
  *   env i of a launch has global id env_id_base + i.  Draws of one accepted step come
@@ -34,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SHIPENV_ABI_VERSION 1
+#define SHIPENV_ABI_VERSION 2
 #define SHIPENV_MAX_PORTS 32      /* ports per world (reference default: 5, utils/constants.py:57-63) */
 #define SHIPENV_MAX_DIM 256       /* map side; coordinates are u8 (reference: 100, shipping/environment.py:29) */
 #define SHIPENV_MAX_CAPACITY 255  /* Initial.MAX_CARGO_CAPACITY upper bound (reference: 50) */
@@ -81,6 +84,13 @@ enum {
 #define SHIPENV_F_AUTO_RESET 1u   /* reset an env in the step that ends its episode (done or truncated) */
 #define SHIPENV_F_ALL_POLICY 2u   /* every action of this call is SHIPENV_ACT_POLICY; `actions` is not read and may
                                      be NULL when only reward_f32 and the three masks are requested */
+#define SHIPENV_F_CHAINED 4u      /* this step may overlap the previous shipenv_step launch of the stream at the launch
+                                     boundary (needs shipenv_step_io.chain; see there).  The caller asserts that every
+                                     input of this call other than ships / clock -- the `actions` array -- was complete
+                                     before that previous launch was enqueued (pre-generated action streams, policy
+                                     steps).  Ignored, i.e. the launch waits for all earlier work of the stream as usual,
+                                     unless the previous launch of this context was a shipenv_step on the same chain
+                                     array and stream that itself took the chain protocol. */
 
 /* One ship, 16 bytes, moved as a single 128-bit load/store.  Mirrors the attributes
  * Environment keeps per ship (shipping/environment.py:37-41). */
@@ -123,6 +133,13 @@ typedef struct {
   double *ep_return;       /* [n] running return of the current episode (read-modify-write) */
   double *stats;           /* [6] episode statistics accumulated at episode end (needs ep_return):
                               sum return, sum return^2, sum length, episodes, max return, min return */
+  uint32_t *chain;         /* NULL, or shipenv_chain_words(n) words of device memory that belong to this (ships, n)
+                              pair: zeroed once by the caller, then only touched by shipenv_step.  With it the step
+                              kernels record, per 256-env unit, how many steps have completed, and a launch flagged
+                              SHIPENV_F_CHAINED starts on a tile as soon as the previous launch has finished that tile
+                              instead of waiting for the whole previous grid (consecutive steps of one env group then
+                              overlap at the launch boundary; any other kernel still sees normal stream order).  Every
+                              shipenv_step on these ships must pass the same array (or none of them may be chained). */
 } shipenv_step_io;
 
 typedef struct shipenv_ctx shipenv_ctx;
@@ -159,6 +176,20 @@ int shipenv_reset(shipenv_ctx *ctx, shipenv_ship *ships, uint32_t *clock, uint64
 int shipenv_step(shipenv_ctx *ctx, shipenv_ship *ships, uint32_t *clock, const int16_t *actions,
                  const shipenv_step_io *io, uint64_t seed, uint64_t env_id_base, int64_t n,
                  int max_steps, uint32_t flags, uint32_t word0, void *stream);
+
+/* T consecutive Environment.step calls per env in one launch -- the loops of the reference's agents,
+ * `for t: env.step(a_t)` (agents/mcts.py:228-236, agents/sarsa.py:222-313), when the T actions of an env are known
+ * up front: actions[t * n + i] (int16 [T, n], NULL with SHIPENV_F_ALL_POLICY: the random policy).  The ship and its
+ * clock stay in registers for the T steps (auto-reset included), so an env-step moves 6 B instead of 46 B and a small
+ * batch is not bound by one launch per step.  Bit-identical to T calls of shipenv_step with word0 = 0.  Outputs, each
+ * nullable: reward / reward_f64 / status / taken [T, n]; done / reset / error ballots [T, ceil(n/32)]. */
+int shipenv_step_many(shipenv_ctx *ctx, shipenv_ship *ships, uint32_t *clock, const int16_t *actions, int T,
+                      float *reward, uint32_t *done_bits, uint32_t *reset_bits, uint32_t *error_bits,
+                      uint8_t *status, int16_t *taken, double *reward_f64, uint64_t seed, uint64_t env_id_base,
+                      int64_t n, int max_steps, uint32_t flags, void *stream);
+
+/* Words of device memory shipenv_step_io.chain needs for n envs. */
+size_t shipenv_chain_words(int64_t n);
 
 /* Environment.sample_action (shipping/environment.py:245-263), one call per env, drawing
  * from word0 of the cell (seed, env, clock).  words_used[i] (nullable) = words consumed;

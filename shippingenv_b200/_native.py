@@ -20,6 +20,7 @@ N_CARGO_ACTIONS = 50
 N_FUEL_ACTIONS = 200
 F_AUTO_RESET = 1
 F_ALL_POLICY = 2
+F_CHAINED = 4
 
 (ST_OK, ST_OFF_MAP, ST_NO_DEST, ST_SEL_RANGE, ST_SEL_ORIGIN, ST_NOT_AT_PORT, ST_BAD_AMOUNT,
  ST_UNKNOWN, ST_NO_PORTS, ST_SAMPLE_CRASH) = range(10)
@@ -47,7 +48,7 @@ class StepIO(C.Structure):
         ("reward_f32", C.c_void_p), ("reward_f64", C.c_void_p),
         ("done_bits", C.c_void_p), ("reset_bits", C.c_void_p), ("error_bits", C.c_void_p),
         ("status", C.c_void_p), ("taken", C.c_void_p), ("obs", C.c_void_p),
-        ("ep_return", C.c_void_p), ("stats", C.c_void_p),
+        ("ep_return", C.c_void_p), ("stats", C.c_void_p), ("chain", C.c_void_p),
     ]
 
 
@@ -66,6 +67,10 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_void_p]),
     "shipenv_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(StepIO), C.c_uint64,
                                C.c_uint64, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "shipenv_chain_words": (C.c_size_t, [C.c_int64]),
+    "shipenv_step_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                    C.c_int64, C.c_int, C.c_uint32, C.c_void_p]),
     "shipenv_step_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(StepIO), C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_uint32,
                                       C.c_uint32, C.c_void_p]),
@@ -106,7 +111,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.shipenv_abi_version() != 1:
+        if handle.shipenv_abi_version() != 2:
             raise ShipEnvError("libshipenv.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib
@@ -214,6 +219,11 @@ class Context:
                     max_steps, flags, word0, stream):
         check(lib().shipenv_step_sample(self._h, ships, clock, actions, C.byref(io), next_action, next_words,
                                         next_status, seed, env_id_base, n, max_steps, flags, word0, stream))
+
+    def step_many(self, ships, clock, actions, T, reward, done, reset, error, status, taken, reward64, seed,
+                  env_id_base, n, max_steps, flags, stream):
+        check(lib().shipenv_step_many(self._h, ships, clock, actions, T, reward, done, reset, error, status, taken,
+                                      reward64, seed, env_id_base, n, max_steps, flags, stream))
 
     def step_host(self, ships, clock, h_actions, h_reward, h_done, h_reset, h_error, workspace, workspace_bytes, seed,
                   env_id_base, n, max_steps, flags, chunks, stream):

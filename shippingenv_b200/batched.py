@@ -9,6 +9,8 @@ exceptions, optional auto-reset, policy actions (-1 = ``sample_action`` until ac
 from dataclasses import dataclass
 from typing import Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -100,6 +102,11 @@ class BatchedEnvironment:
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
             self.stats = new_stats(dev)
         self._policy = None
+        # chained launches (include/shipenv.h, shipenv_step_io.chain): per-unit step counters of this env group
+        self._chain = None
+        if os.environ.get("SHIPENV_NO_CHAIN") != "1":
+            self._chain = torch.zeros(nat.lib().shipenv_chain_words(n), dtype=torch.int32, device=dev)
+        self._chain_ok = False             # cleared whenever the state tensors are written outside step()
         self._host_out = self._host_ws = None
         self.stream, self._stream_handle = None, None
         self._step_cache, self._io_keepalive = {}, []
@@ -121,10 +128,16 @@ class BatchedEnvironment:
     @property
     def fuel(self): return self.ships.view(torch.float64)[:, 1]
 
+    def break_chain(self):
+        """Call after writing ``ships`` / ``clock`` with anything but this object's methods: the next step then waits
+        for all earlier work of its stream even if it is ``chained``."""
+        self._chain_ok = False
+
     def use_stream(self, stream):
         """Launch everything of this environment on ``stream`` (a torch.cuda.Stream) instead of the current stream;
         ``None`` goes back to the current stream.  Independent env groups on separate streams overlap their launch
         boundaries; the caller orders them against producers / consumers of their tensors (wait_stream / events)."""
+        self._chain_ok = False
         self.stream = stream
         self._stream_handle = None if stream is None else stream.cuda_stream
 
@@ -142,14 +155,21 @@ class BatchedEnvironment:
     # ---- the reference API, batched -----------------------------------------------------
     def reset(self, mask_bits=None):
         """``Environment.reset`` for all envs (or those whose mask bit is set)."""
+        self._chain_ok = False
         self.ctx.reset(self.ships.data_ptr(), self.clock.data_ptr(), self.seed, self.env_id_base, self.n,
                        _ptr(mask_bits), self._stream())
         if self.ep_return is not None and mask_bits is None:
             self.ep_return.zero_()
 
     def step(self, actions, want_obs=False, want_status=False, want_taken=False, want_reward64=False,
-             obs_out=None, word0=0):
-        """``Environment.step`` for every env.  ``actions``: int16 [N] flat indices on this device."""
+             obs_out=None, word0=0, chained=False):
+        """``Environment.step`` for every env.  ``actions``: int16 [N] flat indices on this device.
+
+        ``chained=True`` lets this launch overlap the previous ``step`` of this environment at the launch boundary
+        (``SHIPENV_F_CHAINED``): tile i starts as soon as the previous step has finished tile i, instead of after the
+        whole previous grid.  Only for ``actions`` that were complete before the previous step was enqueued
+        (pre-generated action streams); policy steps (``step_policy``) are always chained, they read no actions.
+        Results are identical either way."""
         if actions.dtype != torch.int16 or actions.device != self.device or actions.numel() != self.n:
             raise ValueError("actions must be an int16 tensor of shape [num_envs] on the env's device")
         if not actions.is_contiguous():
@@ -164,6 +184,9 @@ class BatchedEnvironment:
                                                                  obs_out)
         io_ref, res = cached
         flags = (nat.F_AUTO_RESET if self.auto_reset else 0) | (nat.F_ALL_POLICY if actions is self._policy else 0)
+        if (chained or actions is self._policy) and self._chain_ok:
+            flags |= nat.F_CHAINED         # the library honours it only right behind another step of this env
+        self._chain_ok = True
         rc = self._lib_step(self._ctx_handle, self._ships_ptr, self._clock_ptr, actions.data_ptr(), io_ref, self.seed,
                             self.env_id_base, self.n, self.max_steps, flags,
                             word0, self._stream())
@@ -195,6 +218,8 @@ class BatchedEnvironment:
             io.obs = res.obs.data_ptr()
         if self.ep_return is not None:
             io.ep_return, io.stats = self.ep_return.data_ptr(), self.stats.data_ptr()
+        if self._chain is not None:
+            io.chain = self._chain.data_ptr()
         self._io_keepalive.append(io)
         return ctypes.byref(io), res
 
@@ -245,13 +270,51 @@ class BatchedEnvironment:
         if actions.dim() != 2 or actions.shape[1] != self.n or actions.dtype != torch.int16:
             raise ValueError("actions must be an int16 tensor of shape [T, num_envs]")
         rows = [actions[t] for t in range(actions.shape[0])]
+        self._chain_ok = False
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for row in rows:
-                self.step(row, **kw)
+            for row in rows:                      # the whole [T, N] block exists already: steps 1.. may chain
+                self.step(row, chained=True, **kw)
         graph._shipenv_keepalive = (actions, rows)
+        self._chain_ok = False
         return graph
+
+    def step_many(self, actions=None, steps=None, want_status=False, want_taken=False, want_reward64=False,
+                  want_masks=True):
+        """``steps`` consecutive ``Environment.step`` calls per env in ONE launch (``shipenv_step_many``): the ships stay
+        in registers between steps.  ``actions``: int16 [T, N] on this device, or ``None`` for T = ``steps`` steps of
+        the random policy.  Same results as T calls of :meth:`step`.  Returns a dict of [T, ...] tensors: ``reward``
+        float32 [T, N], ``done_bits`` / ``reset_bits`` / ``error_bits`` int32 [T, ceil(N/32)], optionally ``status``,
+        ``taken``, ``reward64``."""
+        if actions is not None:
+            if actions.dim() != 2 or actions.shape[1] != self.n or actions.dtype != torch.int16 \
+                    or actions.device != self.device:
+                raise ValueError("actions must be an int16 tensor of shape [T, num_envs] on the env's device")
+            actions = actions.contiguous()
+            T = actions.shape[0]
+        else:
+            if steps is None:
+                raise ValueError("give `actions` [T, N] or `steps` (random policy)")
+            T = int(steps)
+        dev, n, nw = self.device, self.n, (self.n + 31) // 32
+        out = dict(reward=torch.empty((T, n), dtype=torch.float32, device=dev))
+        if want_masks:
+            for k in ("done_bits", "reset_bits", "error_bits"):
+                out[k] = torch.empty((T, nw), dtype=torch.int32, device=dev)
+        if want_status:
+            out["status"] = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        if want_taken:
+            out["taken"] = torch.empty((T, n), dtype=torch.int16, device=dev)
+        if want_reward64:
+            out["reward64"] = torch.empty((T, n), dtype=torch.float64, device=dev)
+        flags = (nat.F_AUTO_RESET if self.auto_reset else 0) | (nat.F_ALL_POLICY if actions is None else 0)
+        self._chain_ok = False
+        self.ctx.step_many(self._ships_ptr, self._clock_ptr, _ptr(actions), T, out["reward"].data_ptr(),
+                           _ptr(out.get("done_bits")), _ptr(out.get("reset_bits")), _ptr(out.get("error_bits")),
+                           _ptr(out.get("status")), _ptr(out.get("taken")), _ptr(out.get("reward64")), self.seed,
+                           self.env_id_base, n, self.max_steps, flags, self._stream())
+        return out
 
     def step_policy(self, **kw):
         """One step of the reference's random policy (``sample_action`` + retry) on every env."""
@@ -342,6 +405,7 @@ class BatchedEnvironment:
     # ---- host <-> device state ----------------------------------------------------------
     def load_state(self, ships_np, clock_np=None):
         """Overwrite the ship records (numpy structured/uint8 [N,16]) and optionally the clock."""
+        self._chain_ok = False
         raw = np.ascontiguousarray(ships_np).view(np.uint8).reshape(self.n, 16)
         self.ships.copy_(torch.from_numpy(raw))
         if clock_np is not None:

@@ -2,6 +2,7 @@
 //   pipeline.cuh          constants + PTX helpers (mbarrier, TMA bulk copies, world staging)
 //   step_kernels.cuh      general step kernel (all outputs, any action)
 //   step_fast_kernels.cuh throughput step kernels (the roofline kernel of bench.py)
+//   step_many_kernels.cuh T steps per launch with the ship in registers (shipenv_step_many)
 //   aux_kernels.cuh       reset / observe / sample_action / valid-action mask / discretize
 //   mcts_kernels.cuh      rollouts and the full MCTS choose_action
 //
@@ -13,5 +14,6 @@
 #include "pipeline.cuh"
 #include "step_kernels.cuh"
 #include "step_fast_kernels.cuh"
+#include "step_many_kernels.cuh"
 #include "aux_kernels.cuh"
 #include "mcts_kernels.cuh"

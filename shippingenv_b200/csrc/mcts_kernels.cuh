@@ -6,6 +6,117 @@
 namespace shipenv {
 
 // ------------------------------------------------------------------------------------------
+// One attempt of the rollout loop body `a = env.sample_action(); env.step(a)` (agents/mcts.py:229-236) as
+// straight-line code, so that the 32 rollouts of a warp stay converged.
+//
+// Rollouts from roots near a port (BASELINE configs[3]: post-reset ships advanced by 10 random moves) are full of
+// what the stepping kernels treat as rare events: TAKE_CARGO every time the ship stands on a port with an empty
+// hold, a cargo-loss draw with probability cargo / 50 on every move after that.  Executed as branches, each of them
+// idles most of the warp (22 of 32 lanes active on aged roots, fewer near ports).  Here every lane looks at the next
+// seven words of its stream (g.ensure(7) has been called: move choice, fuel cost, loss trigger, loss quantile, three
+// beta draws), evaluates the whole MOVE with selects, and advances the stream by what the reference would have
+// consumed.  Branches remain only for what really is rare: TAKE_CARGO (needs the port scan), an off-map choice
+// (re-drawn), an arrival (destination re-draw loop), and states the reference's sample_action treats differently
+// (no destination, fuel == 0 at a port), which go to the general code.
+// Returns 0 = step accepted, 1 = rejected (the draw is consumed, the agents' loop tries again),
+//         2 = not handled here, nothing consumed.
+// ------------------------------------------------------------------------------------------
+template <class G>
+__device__ __forceinline__ int rollout_attempt(const WorldView& w, ShipR& s, G& g, double& reward, bool& done) {
+  const int W = w.h->W, H = w.h->H, cap = w.h->capacity;
+  if (s.dest == kNone || s.cargo < 0 || unsigned(s.x) >= unsigned(W) || unsigned(s.y) >= unsigned(H)) return 2;
+  const bool on_port = w.port_cell(s.x, s.y);
+  const uint32_t w0 = g.peek(0);
+  if (on_port) {                                       // sample_action looks at the port first (:247-260)
+    if (s.cargo != 0) {
+      if (s.fuel == 0.0) return 2;                     // :258-260 -> :163
+    } else {                                           // TAKE_CARGO randint(1, stock) (:255-257, :341-348)
+      const int stock = int(w.h->port[current_port(w, s)] >> 24);
+      if (stock == 0) return 2;                        // randint(1, 0): the general code rejects it
+      s.cargo += 1 + int(__umulhi(w0, uint32_t(stock)));
+      reward = w.h->r_take_cargo;
+      done = false;
+      g.advance(1);
+      return 0;
+    }
+  }
+  const int m = int(__umulhi(w0, 4u));                 // choice([N, E, S, W]) (:165-167)
+  const int dx = (m & 1) * (m - 2), dy = ((m & 1) ^ 1) * (m - 1);
+  const int nx = s.x + dx, ny = s.y + dy;
+  if (unsigned(nx) >= unsigned(W) || unsigned(ny) >= unsigned(H)) { g.advance(1); return 1; }   // :284
+  const uint32_t w1 = g.peek(1), w2 = g.peek(2), w3 = g.peek(3), w4 = g.peek(4), w5 = g.peek(5), w6 = g.peek(6);
+  const double cost = __dadd_rn(1.0, __dadd_rn(-0.1, __dmul_rn(0.1 - (-0.1), unit_double(w1))));   // :287, :103-104
+  const bool no_fuel = s.fuel < cost;                                                   // :288
+  const bool water = w.passable(nx, ny);                                                // :293
+  const uint32_t pd = w.h->port[s.dest];
+  const int tx = pd & 255u, ty = (pd >> 8) & 255u;
+  const bool closer = (s.x - tx) * dx + (s.y - ty) * dy < 0;                            // :307-315, unit move
+  s.x = water ? nx : s.x; s.y = water ? ny : s.y;                                       // :297
+  s.fuel = water ? __dsub_rn(s.fuel, cost) : s.fuel;                                    // :298
+  double r = w.h->move_reward[(int(no_fuel) << 2) | (int(!water) << 1) | int(closer)];
+  // cargo loss (:318-323, :169-200): trigger word, quantile word, median of three words for betavariate(2, 2)
+  const bool trigger = w2 <= w.h->loss_thr[min(s.cargo, cap)];
+  const double q = unit_double(w3);
+  const bool lose_none = q < 0.1, lose_all = q > 0.9;
+  const uint32_t med = max(min(w4, w5), min(max(w4, w5), w6));
+  const int part = __double2int_rz(__dmul_rn(unit_double(med), double(s.cargo)));
+  const bool has_cargo = s.cargo != 0;
+  const int loss = (!has_cargo || lose_none) ? 0 : lose_all ? s.cargo : part;
+  const double r_loss = __dadd_rn(r, __dmul_rn(double(loss), w.h->p_loss));
+  r = trigger ? r_loss : r;
+  s.cargo -= trigger ? loss : 0;
+  g.advance(3u + (trigger ? 1u : 0u) + ((trigger && has_cargo && !lose_none && !lose_all) ? 3u : 0u));
+  if (s.x == tx && s.y == ty) {                                                         // arrival, :325-337
+    r = __dadd_rn(r, __dmul_rn(double(s.cargo), w.h->r_deliver));
+    s.cargo = 0;
+    s.origin = s.dest;
+    const int P = w.h->P;
+    int d = g.randint(0, P - 1);
+    while (d == s.origin && P > 1) d = g.randint(0, P - 1);
+    s.dest = P > 1 ? d : kNone;
+    r = __dadd_rn(r, w.h->r_arrive);
+  }
+  reward = r;
+  done = no_fuel;
+  return 0;
+}
+
+// MCTSAgent._rollout (agents/mcts.py:211-238) from ship s on stream g: at most L accepted steps.
+// Returns the status (SHIPENV_ST_OK unless the rollout had to stop); total / steps by reference.
+template <class G>
+__device__ __forceinline__ int rollout_run(const WorldView& w, ShipR& s, G& g, int L, double& total, int& steps) {
+  total = 0.0;                                     // agents/mcts.py:224
+  steps = 0;
+  bool done = false;
+  int fails = 0;
+  while (!done && steps < L) {                     // agents/mcts.py:228
+    g.ensure(7);
+    double reward = 0.0;
+    int rc = w.h->P == 0 ? 2 : rollout_attempt(w, s, g, reward, done);
+    if (rc == 2) {                                 // the general code: every state the reference can be in
+      if (w.h->P == 0) return SHIPENV_ST_NO_PORTS;
+      if (s.dest == kNone && current_port(w, s) < 0) return SHIPENV_ST_NO_DEST;
+      int cat, val;
+      if (sample_action(w, s, g, cat, val) != SHIPENV_ST_OK) return SHIPENV_ST_SAMPLE_CRASH;
+      const int e = do_action(w, s, g, cat, val, reward, done);
+      if (e != SHIPENV_ST_OK) {                    // agents/mcts.py:234-236: try another
+        done = false;
+        if (++fails >= kMaxTries) return e;
+        continue;
+      }
+    } else if (rc == 1) {
+      done = false;
+      if (++fails >= kMaxTries) return SHIPENV_ST_OFF_MAP;
+      continue;
+    }
+    fails = 0;
+    total = __dadd_rn(total, reward);
+    ++steps;
+  }
+  return SHIPENV_ST_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // MCTS rollouts: the whole simulations x max_rollout_steps loop in one kernel
 // ------------------------------------------------------------------------------------------
 struct RolloutArgs {
@@ -23,7 +134,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
-  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [8][blockDim.x] words
+  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [16][blockDim.x] words
   const int64_t total = a.R * int64_t(a.S);
   const int64_t n_tiles = (total + kRolloutThreads - 1) / kRolloutThreads;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -34,26 +145,9 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
     ShipR s = unpack(__ldg(a.roots + r));
     RngFifo g;
     g.seek(a.round_key, fifo + threadIdx.x, blockDim.x, uint32_t(sim), a.root_id_base + uint64_t(r));
-    double total_reward = 0.0;                     // agents/mcts.py:224
-    bool done = false;
-    int steps = 0, st = SHIPENV_ST_OK, fails = 0;
-    while (!done && steps < a.L) {                 // agents/mcts.py:228
-      g.ensure();
-      if (w.h->P == 0) { st = SHIPENV_ST_NO_PORTS; break; }
-      if (s.dest == kNone && current_port(w, s) < 0) { st = SHIPENV_ST_NO_DEST; break; }
-      int cat, val;
-      if (sample_action(w, s, g, cat, val) != SHIPENV_ST_OK) { st = SHIPENV_ST_SAMPLE_CRASH; break; }
-      double reward = 0.0;
-      const int e = do_action(w, s, g, cat, val, reward, done);
-      if (e != SHIPENV_ST_OK) {                    // agents/mcts.py:234-236: try another
-        done = false;
-        if (++fails >= kMaxTries) { st = e; break; }
-        continue;
-      }
-      fails = 0;
-      total_reward = __dadd_rn(total_reward, reward);
-      ++steps;
-    }
+    double total_reward;
+    int steps;
+    const int st = rollout_run(w, s, g, a.L, total_reward, steps);
     a.returns[j] = total_reward;
     if (a.final) a.final[j] = pack(s);
     if (a.steps) a.steps[j] = steps;
@@ -62,27 +156,33 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------
-// MCTS: the whole choose_action (agents/mcts.py:240-292) per root in one thread, tree in local memory
+// MCTS: the whole choose_action (agents/mcts.py:240-292) per root in one thread
 // ------------------------------------------------------------------------------------------
-constexpr int kMctsMaxNodes = SHIPENV_MCTS_MAX_SIMS + 2;
-constexpr int kMctsThreads = 128;
+constexpr int kMctsThreads = 64;
 
 struct MctsArgs {
   const void* world; uint32_t world_bytes;
   const uint4* roots; int64_t R; int S, L;
   double c_param;
-  const double* log_table;     // device, log_table[n] = log(n)
   int16_t* action; int32_t* root_visits; int16_t* child_action; int32_t* child_visits; double* child_total;
   uint8_t* status;
   uint64_t seed, root_id_base;
   uint32_t round_key[20];
+  double log_table[SHIPENV_MCTS_MAX_SIMS + 2];   // log_table[n] = log(n) as the caller computes it (numpy.log)
 };
 
-struct MctsTree {              // one root's tree (agents/mcts.py:13-40), indexed by node id
-  double total[kMctsMaxNodes];
-  uint16_t visits[kMctsMaxNodes];
-  uint8_t parent[kMctsMaxNodes], action[kMctsMaxNodes], nchild[kMctsMaxNodes], moves_ok[kMctsMaxNodes];
-  uint8_t child[kMctsMaxNodes][4];
+// One root's tree (agents/mcts.py:13-40), indexed by node id; at most one node per simulation plus the root, so the
+// arrays are sized by the launch's S (kNodes = 64 covers the reference's 50 simulations, 128 the ABI maximum).
+template <int kNodes>
+struct MctsTree {
+  double total[kNodes];
+  uint8_t visits[kNodes];       // <= S <= 126
+  uint8_t parent[kNodes];
+  uint8_t info[kNodes];         // action (2 bits) | nchild << 2 (3 bits) | moves_ok << 5
+  uint8_t child[kNodes][4];
+  __device__ __forceinline__ int action(int n) const { return info[n] & 3; }
+  __device__ __forceinline__ int nchild(int n) const { return (info[n] >> 2) & 7; }
+  __device__ __forceinline__ bool moves_ok(int n) const { return info[n] & 32; }
 };
 
 // get_possible_actions (:50-89) is the four moves iff a destination is set and not (fuel == 0 with an origin)
@@ -91,11 +191,13 @@ __device__ __forceinline__ bool mcts_moves_ok(const ShipR& s) {
 }
 
 // best_child (:109-128): UCB1, unvisited children first, np.argmax takes the first maximum
-__device__ __forceinline__ int mcts_best_child(const MctsTree& t, int node, double c_param, const double* log_table) {
+template <int kNodes>
+__device__ __forceinline__ int mcts_best_child(const MctsTree<kNodes>& t, int node, double c_param, const double* log_table) {
   int best = 0;
   double best_v = 0.0;
   const double two_log = __dmul_rn(2.0, log_table[t.visits[node]]);
-  for (int k = 0; k < t.nchild[node]; ++k) {
+  const int nc = t.nchild(node);
+  for (int k = 0; k < nc; ++k) {
     const int ch = t.child[node][k];
     double v;
     if (t.visits[ch] == 0) v = __longlong_as_double(0x7FF0000000000000LL);
@@ -108,18 +210,22 @@ __device__ __forceinline__ int mcts_best_child(const MctsTree& t, int node, doub
   return best;
 }
 
+template <int kNodes>
 __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constant__ MctsArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
-  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [8][blockDim.x] words
+  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [16][blockDim.x] words
+  double* log_table = reinterpret_cast<double*>(fifo + RngFifo::kWords * kMctsThreads);
+  for (int k = threadIdx.x; k < a.S + 2; k += kMctsThreads) log_table[k] = a.log_table[k];
+  __syncthreads();
   for (int64_t r = blockIdx.x * int64_t(kMctsThreads) + threadIdx.x; r < a.R; r += int64_t(gridDim.x) * kMctsThreads) {
     const ShipR root = unpack(__ldg(a.roots + r));
-    MctsTree t;
+    MctsTree<kNodes> t;
     int n_nodes = 1, st = SHIPENV_ST_OK;
-    t.total[0] = 0.0; t.visits[0] = 0; t.parent[0] = 255; t.action[0] = 255; t.nchild[0] = 0;
-    t.moves_ok[0] = mcts_moves_ok(root);
+    t.total[0] = 0.0; t.visits[0] = 0; t.parent[0] = 255;
+    t.info[0] = uint8_t(mcts_moves_ok(root) ? 32 : 0);
     for (int sim = 0; sim < a.S && st == SHIPENV_ST_OK; ++sim) {
       ShipR s = root;                                                        // _create_env_copy, :257
       RngFifo g;
@@ -128,17 +234,18 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
       bool done = false;
       double rew = 0.0;
       for (;;) {                                                             // selection, :260-268
-        if (!t.moves_ok[node]) { st = SHIPENV_ST_MCTS_UNSUPPORTED; break; }
-        if (t.nchild[node] != 4) break;
+        if (!t.moves_ok(node)) { st = SHIPENV_ST_MCTS_UNSUPPORTED; break; }
+        if (t.nchild(node) != 4) break;
         g.ensure();
-        node = mcts_best_child(t, node, a.c_param, a.log_table);
-        const int e = do_action(w, s, g, kCatMove, t.action[node], rew, done);
+        node = mcts_best_child(t, node, a.c_param, log_table);
+        const int e = do_action(w, s, g, kCatMove, t.action(node), rew, done);
         if (e != SHIPENV_ST_OK || done) break;
       }
       if (st != SHIPENV_ST_OK) break;
       // expansion, :271-279: untried actions in the order N, S, E, W (:80-87) = flat indices 0, 2, 1, 3
       uint32_t tried = 0;
-      for (int k = 0; k < t.nchild[node]; ++k) tried |= 1u << t.action[t.child[node][k]];
+      const int nc = t.nchild(node);
+      for (int k = 0; k < nc; ++k) tried |= 1u << t.action(t.child[node][k]);
       const int n_un = 4 - __popc(tried);
       if (n_un > 0) {
         g.ensure();
@@ -150,42 +257,32 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
         const int e = do_action(w, s, g, kCatMove, act, rew, done);
         if (e != SHIPENV_ST_OK) continue;                                    // :278-279: the simulation is skipped
         const int ch = n_nodes++;
-        t.total[ch] = rew; t.visits[ch] = 0; t.parent[ch] = uint8_t(node); t.action[ch] = uint8_t(act);   // :144-146
-        t.nchild[ch] = 0; t.moves_ok[ch] = mcts_moves_ok(s);
-        t.child[node][t.nchild[node]++] = uint8_t(ch);
+        t.total[ch] = rew; t.visits[ch] = 0; t.parent[ch] = uint8_t(node);   // :144-146
+        t.info[ch] = uint8_t(act | (mcts_moves_ok(s) ? 32 : 0));
+        t.child[node][nc] = uint8_t(ch);
+        t.info[node] = uint8_t(t.info[node] + 4);                            // one more child
         node = ch;
       }
       // simulation: _rollout, :211-238, continuing the same word stream
-      double total = 0.0;
-      bool rdone = false;
-      int steps = 0, fails = 0;
-      while (!rdone && steps < a.L) {
-        g.ensure();
-        if (s.dest == kNone && current_port(w, s) < 0) { st = SHIPENV_ST_NO_DEST; break; }
-        int cat, val;
-        if (sample_action(w, s, g, cat, val) != SHIPENV_ST_OK) { st = SHIPENV_ST_SAMPLE_CRASH; break; }
-        double rr = 0.0;
-        const int e = do_action(w, s, g, cat, val, rr, rdone);
-        if (e != SHIPENV_ST_OK) { rdone = false; if (++fails >= kMaxTries) { st = e; break; } continue; }
-        fails = 0;
-        total = __dadd_rn(total, rr);
-        ++steps;
-      }
+      double total;
+      int steps;
+      st = rollout_run(w, s, g, a.L, total, steps);
       if (st != SHIPENV_ST_OK) break;
       for (int n = node; n != 255; n = t.parent[n]) { t.visits[n] += 1; t.total[n] = __dadd_rn(t.total[n], total); }   // :149-159
     }
+    const int nc0 = t.nchild(0);
     for (int k = 0; k < 4; ++k) {
-      const bool has = k < t.nchild[0];
+      const bool has = k < nc0;
       const int ch = has ? t.child[0][k] : 0;
-      a.child_action[4 * r + k] = has ? int16_t(t.action[ch]) : int16_t(-1);
+      a.child_action[4 * r + k] = has ? int16_t(t.action(ch)) : int16_t(-1);
       a.child_visits[4 * r + k] = has ? int32_t(t.visits[ch]) : 0;
       a.child_total[4 * r + k] = has ? t.total[ch] : 0.0;
     }
     a.root_visits[r] = t.visits[0];
     int act = -1;
     if (st == SHIPENV_ST_OK) {
-      if (t.nchild[0] == 0) st = SHIPENV_ST_MCTS_NO_CHILDREN;                // :291-292
-      else act = t.action[mcts_best_child(t, 0, 0.0, a.log_table)];          // :288-290
+      if (nc0 == 0) st = SHIPENV_ST_MCTS_NO_CHILDREN;                        // :291-292
+      else act = t.action(mcts_best_child(t, 0, 0.0, log_table));            // :288-290
     }
     a.action[r] = int16_t(act);
     a.status[r] = uint8_t(st);

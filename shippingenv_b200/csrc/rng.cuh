@@ -90,17 +90,20 @@ struct Rng {
   }
 };
 
-// The same word stream behind a small FIFO in shared memory (8 words per thread, word-interleaved so that the
+// The same word stream behind a small FIFO in shared memory (16 words per thread, word-interleaved so that the
 // threads of a warp never conflict).  Long sequential consumers (rollouts, MCTS) call ensure() once per
 // environment step: every lane of the warp then refills at ONE code site, in lock-step, instead of each lane
-// running Philox at whichever of the many next() call sites it happens to cross a block boundary.
+// running Philox at whichever of the many next() call sites it happens to cross a block boundary.  With
+// ensure(k) done, peek(0..k-1) reads ahead without consuming, so a step can be written as straight-line code that
+// looks at every word it might need and then advance()s by what it used.
 struct RngFifo {
+  static constexpr uint32_t kWords = 16;   // ring size per thread
   const uint32_t* rk;
-  uint32_t* slot;          // this thread's column of the shared [8][blockDim.x] word array
+  uint32_t* slot;          // this thread's column of the shared [kWords][blockDim.x] word array
   uint32_t stride;         // blockDim.x
   uint32_t c1, c2, c3;
   uint32_t i;              // next word of the cell to hand out
-  uint32_t filled;         // words generated so far (multiple of 4); words [filled-8, filled) are resident
+  uint32_t filled;         // words generated so far (multiple of 4); words [filled-16, filled) are resident
 
   __device__ __forceinline__ void seek(const uint32_t* round_keys, uint32_t* column, uint32_t column_stride,
                                        uint32_t cell1, uint64_t id) {
@@ -111,16 +114,18 @@ struct RngFifo {
   __device__ __forceinline__ void refill() {
     uint32_t w[4];
     philox4x32_10(filled >> 2, c1, c2, c3, rk[0], rk[1], w);
-    const uint32_t base = filled & 7u;                 // 0 or 4
+    const uint32_t base = filled & (kWords - 1u);      // 0, 4, 8 or 12
 #pragma unroll
     for (int k = 0; k < 4; ++k) slot[(base + k) * stride] = w[k];
     filled += 4;
   }
-  // at least 4 words ahead: the common step (choice, fuel cost, loss draw) then never refills inside
-  __device__ __forceinline__ void ensure() { if (filled - i < 4u) refill(); }
+  // at least `ahead` (<= 8) words resident beyond the read position
+  __device__ __forceinline__ void ensure(uint32_t ahead = 4u) { while (filled - i < ahead) refill(); }
+  __device__ __forceinline__ uint32_t peek(uint32_t k) const { return slot[((i + k) & (kWords - 1u)) * stride]; }
+  __device__ __forceinline__ void advance(uint32_t k) { i += k; }
   __device__ __forceinline__ uint32_t next() {
     if (i == filled) refill();                         // rare: a step that needs more than the words ahead
-    const uint32_t w = slot[(i & 7u) * stride];
+    const uint32_t w = slot[(i & (kWords - 1u)) * stride];
     ++i;
     return w;
   }

@@ -9,7 +9,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "kernels.cuh"
@@ -55,7 +58,10 @@ const shipenv_consts kDefaultConsts = {
 }  // namespace
 
 constexpr int kHostStreams = 4;                 // chunks of one shipenv_step_host call in flight
-constexpr int kTicketSlots = 1 + kHostStreams;   // slot 0: shipenv_step; 1..: the chunks
+// Tile-ticket counters of step_fast_kernel launches that carry no chain array: a ring, one slot per launch in
+// issue order, so that launches of one context that are in flight together (other streams, the chunks of
+// shipenv_step_host) never share a counter unless more than kTicketSlots of them overlap.
+constexpr int kTicketSlots = 64;
 constexpr int kTicketStride = 32;                // uint32 words between counters
 
 struct shipenv_ctx {
@@ -69,9 +75,18 @@ struct shipenv_ctx {
   shipenv_consts consts = kDefaultConsts;
   // device blob
   void* d_world = nullptr;
-  double* d_log_table = nullptr;        // shipenv_mcts: log(n), n = 0..SHIPENV_MCTS_MAX_SIMS+1
-  uint32_t* d_tile_counter = nullptr;   // ticket counters of step_fast_kernel's tile scheduler (self-resetting), one
-                                        // per launch that may be in flight at a time, 128 bytes apart
+  uint32_t* d_tile_counter = nullptr;   // ticket counters of step_fast_kernel's tile scheduler (self-resetting), a
+                                        // ring of kTicketSlots, 128 bytes apart
+  std::atomic<uint32_t> ticket_next{0};
+  // chained launches: the chain array, stream and capture status of the last launch of this context when that
+  // launch took the chain protocol (null otherwise) -- SHIPENV_F_CHAINED is honoured only right after such a launch
+  uint32_t* last_chain = nullptr;
+  cudaStream_t last_chain_stream = nullptr;
+  bool last_chain_capturing = false;
+  // the world upload: other streams wait for it until it has completed
+  cudaEvent_t world_event = nullptr;
+  cudaStream_t world_stream = nullptr;
+  bool world_pending = false;
   // shipenv_step_host: internal streams and events, created on first use
   cudaStream_t host_stream[kHostStreams] = {};
   cudaEvent_t host_fork = nullptr, host_join[kHostStreams] = {};
@@ -82,7 +97,7 @@ struct shipenv_ctx {
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_fast[8], occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_step_sample, occ_rollout, occ_valid, occ_mcts;
+  Occ occ_fast[8], occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_step_sample, occ_rollout, occ_valid, occ_mcts[2], occ_many[6];
 };
 
 namespace {
@@ -140,22 +155,61 @@ int build_world(shipenv_ctx* c) {
   return 0;
 }
 
-int sync_world(shipenv_ctx* c, cudaStream_t stream) {
-  if (!c->dirty) return 0;
-  if (int rc = build_world(c)) return rc;
-  // pageable source: the runtime stages the bytes before returning, so h_world may change later
-  CUDA_TRY(cudaMemcpyAsync(c->d_world, c->h_world.data(), c->world_bytes, cudaMemcpyHostToDevice, stream));
-  c->dirty = false;
+// Called by every launch.  `chain` = the chain array when the launch takes the chain protocol, else null (any
+// other launch of the context ends a chain: the next SHIPENV_F_CHAINED request is not honoured).
+int sync_world(shipenv_ctx* c, cudaStream_t stream, uint32_t* chain = nullptr) {
+  c->last_chain = chain;
+  c->last_chain_stream = stream;
+  if (c->dirty) {
+    if (int rc = build_world(c)) return rc;
+    // pageable source: the runtime stages the bytes before returning, so h_world may change later
+    CUDA_TRY(cudaMemcpyAsync(c->d_world, c->h_world.data(), c->world_bytes, cudaMemcpyHostToDevice, stream));
+    // launches on other streams must not read the blob before the upload has landed
+    if (!c->world_event) CUDA_TRY(cudaEventCreateWithFlags(&c->world_event, cudaEventDisableTiming));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    c->world_pending = false;
+    if (cap == cudaStreamCaptureStatusNone) {
+      CUDA_TRY(cudaEventRecord(c->world_event, stream));
+      c->world_stream = stream;
+      c->world_pending = true;
+    }
+    c->dirty = false;
+  } else if (c->world_pending && stream != c->world_stream) {
+    // (not while `stream` is being captured: a capture may not wait on outside work -- and it begins with the device
+    // idle, so the upload has landed)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      if (cudaEventQuery(c->world_event) == cudaSuccess) c->world_pending = false;
+      else CUDA_TRY(cudaStreamWaitEvent(stream, c->world_event, 0));
+    }
+  }
+  return 0;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (device, function), not to a context: it only ever rises,
+// whatever order contexts with different worlds launch in.
+std::mutex g_optin_mutex;
+std::map<std::pair<int, const void*>, size_t> g_optin;
+
+template <class Kernel>
+int raise_smem_optin(shipenv_ctx* c, Kernel kernel, size_t smem) {
+  if (smem <= 48 * 1024) return 0;
+  if (smem > size_t(c->max_smem_optin)) return fail(SHIPENV_E_ARG, "needs %zu B of shared memory per CTA", smem);
+  std::lock_guard<std::mutex> lock(g_optin_mutex);
+  size_t& have = g_optin[{c->device, reinterpret_cast<const void*>(kernel)}];
+  if (smem > have) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    have = smem;
+  }
   return 0;
 }
 
 template <class Kernel>
 int grid_for(shipenv_ctx* c, Kernel kernel, shipenv_ctx::Occ& occ, int threads, size_t smem, int64_t tiles, int* grid) {
   if (occ.smem != smem) {
-    if (smem > 48 * 1024) {
-      if (smem > size_t(c->max_smem_optin)) return fail(SHIPENV_E_ARG, "needs %zu B of shared memory per CTA", smem);
-      CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    }
+    if (int rc = raise_smem_optin(c, kernel, smem)) return rc;
     int blocks = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, threads, smem));
     if (blocks < 1) return fail(SHIPENV_E_CUDA, "kernel does not fit an SM");
@@ -234,11 +288,13 @@ int shipenv_ctx_create(int device, shipenv_ctx** out) {
   CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   cudaError_t e = cudaMalloc(&c->d_world, kMaxWorldBytes);
   if (e != cudaSuccess) { delete c; return fail(SHIPENV_E_CUDA, "cudaMalloc(world): %s", cudaGetErrorString(e)); }
-  e = cudaMalloc(&c->d_log_table, sizeof(double) * (SHIPENV_MCTS_MAX_SIMS + 2));
-  if (e != cudaSuccess) { cudaFree(c->d_world); delete c; return fail(SHIPENV_E_CUDA, "log table: %s", cudaGetErrorString(e)); }
   e = cudaMalloc(&c->d_tile_counter, kTicketSlots * kTicketStride * 4);
   if (e == cudaSuccess) e = cudaMemset(c->d_tile_counter, 0, kTicketSlots * kTicketStride * 4);
-  if (e != cudaSuccess) { cudaFree(c->d_world); delete c; return fail(SHIPENV_E_CUDA, "tile counter: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) {
+    cudaFree(c->d_world); if (c->d_tile_counter) cudaFree(c->d_tile_counter);
+    delete c;
+    return fail(SHIPENV_E_CUDA, "tile counter: %s", cudaGetErrorString(e));
+  }
   *out = c;
   return 0;
 }
@@ -249,7 +305,7 @@ int shipenv_ctx_destroy(shipenv_ctx* c) {
     DeviceGuard guard(c->device);
     if (c->d_world) cudaFree(c->d_world);
     if (c->d_tile_counter) cudaFree(c->d_tile_counter);
-    if (c->d_log_table) cudaFree(c->d_log_table);
+    if (c->world_event) cudaEventDestroy(c->world_event);
     if (c->host_ready) {
       for (int k = 0; k < kHostStreams; ++k) { cudaStreamDestroy(c->host_stream[k]); cudaEventDestroy(c->host_join[k]); }
       cudaEventDestroy(c->host_fork);
@@ -321,11 +377,10 @@ int shipenv_reset(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, uint64_t
   return 0;
 }
 
-// shipenv_step proper.  `ticket_slot` selects the tile-ticket counter: launches that may run concurrently on one
-// context (the chunks of shipenv_step_host) must not share one.
+// shipenv_step proper.
 static int step_impl(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* actions,
                      const shipenv_step_io* io, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
-                     uint32_t flags, uint32_t word0, cudaStream_t stream, int ticket_slot) {
+                     uint32_t flags, uint32_t word0, cudaStream_t stream) {
   if (int rc = check_ctx(c)) return rc;
   const bool all_policy = flags & SHIPENV_F_ALL_POLICY;
   if (n < 0 || (n > 0 && (!ships || !clock || (!actions && !all_policy)))) return fail(SHIPENV_E_ARG, "step: null buffer or negative n");
@@ -336,6 +391,10 @@ static int step_impl(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const
     return fail(SHIPENV_E_ARG, "step: ships, clock and actions must be 16-byte aligned (TMA bulk copies)");
   if ((flags & SHIPENV_F_AUTO_RESET) && c->P < 2) return fail(SHIPENV_E_STATE, "auto-reset needs at least 2 ports");
   DeviceGuard guard(c->device);
+  // what the previous launch of this context was, before sync_world() forgets it
+  uint32_t* const prev_chain = c->last_chain;
+  const cudaStream_t prev_chain_stream = c->last_chain_stream;
+  const bool prev_chain_capturing = c->last_chain_capturing;
   if (int rc = sync_world(c, stream)) return rc;
   StepArgs a{};
   a.world = c->d_world; a.world_bytes = c->world_bytes;
@@ -371,10 +430,25 @@ static int step_impl(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const
     }
     shipenv_ctx::Occ* occ = &c->occ_fast[variant];
     const int64_t fast_tiles = (n + int64_t(kThreads) * ept - 1) / (int64_t(kThreads) * ept);
-    if (int rc = grid_for(c, kernel, *occ, kStepBlock, smem, fast_tiles, &grid)) return rc;
-    a.tile_counter = c->d_tile_counter + ticket_slot * kTicketStride;
+    if (int rc = grid_for(c, kernel, *occ, kFastBlock, smem, fast_tiles, &grid)) return rc;
+    a.tile_counter = c->d_tile_counter + (c->ticket_next.fetch_add(1) % kTicketSlots) * kTicketStride;
+    a.chain = a.io.chain;
+    if (a.chain) {
+      if (reinterpret_cast<uintptr_t>(a.chain) & 7u) return fail(SHIPENV_E_ARG, "step: chain must be 8-byte aligned");
+      // SHIPENV_F_CHAINED is honoured only directly behind a chain-protocol launch on the same array and stream
+      // (and not across the end of a stream capture); otherwise this launch waits for everything before it
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cap);
+      const bool capturing = cap != cudaStreamCaptureStatusNone;
+      if (!(prev_chain == a.chain && prev_chain_stream == stream && prev_chain_capturing == capturing))
+        a.flags &= ~SHIPENV_F_CHAINED;
+      c->last_chain = a.chain;
+      c->last_chain_capturing = capturing;
+    } else {
+      a.flags &= ~SHIPENV_F_CHAINED;
+    }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStepBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFastBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this grid's prologue
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // with the previous grid's tail
@@ -413,7 +487,48 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
                  const shipenv_step_io* io, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
                  uint32_t flags, uint32_t word0, void* stream_) {
   return step_impl(c, ships, clock, actions, io, seed, env_id_base, n, max_steps, flags, word0,
-                   static_cast<cudaStream_t>(stream_), 0);
+                   static_cast<cudaStream_t>(stream_));
+}
+
+size_t shipenv_chain_words(int64_t n) {
+  if (n <= 0) return 0;
+  return size_t(kChainEpoch) + size_t((n + kChainUnit - 1) / kChainUnit) + 1;
+}
+
+int shipenv_step_many(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* actions, int T,
+                      float* reward, uint32_t* done_bits, uint32_t* reset_bits, uint32_t* error_bits, uint8_t* status,
+                      int16_t* taken, double* reward_f64, uint64_t seed, uint64_t env_id_base, int64_t n, int max_steps,
+                      uint32_t flags, void* stream_) {
+  if (int rc = check_ctx(c)) return rc;
+  const bool all_policy = flags & SHIPENV_F_ALL_POLICY;
+  if (n < 0 || T < 0 || (n > 0 && T > 0 && (!ships || !clock || (!actions && !all_policy))))
+    return fail(SHIPENV_E_ARG, "step_many: null buffer or negative size");
+  if (max_steps < 0 || max_steps > 65535) return fail(SHIPENV_E_ARG, "max_steps %d outside 0..65535", max_steps);
+  if (n == 0 || T == 0) return 0;
+  if (n >= (int64_t(1) << 31)) return fail(SHIPENV_E_ARG, "step_many: at most 2^31-1 envs per launch");
+  if (reinterpret_cast<uintptr_t>(ships) & 15u) return fail(SHIPENV_E_ARG, "step_many: ships must be 16-byte aligned");
+  if ((flags & SHIPENV_F_AUTO_RESET) && c->P < 2) return fail(SHIPENV_E_STATE, "auto-reset needs at least 2 ports");
+  DeviceGuard guard(c->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = sync_world(c, stream)) return rc;
+  StepManyArgs a{};
+  a.world = c->d_world; a.world_bytes = c->world_bytes;
+  a.ships = reinterpret_cast<uint4*>(ships); a.clock = clock; a.actions = actions;
+  a.reward = reward; a.done_bits = done_bits; a.reset_bits = reset_bits; a.error_bits = error_bits;
+  a.status = status; a.taken = taken; a.reward_f64 = reward_f64;
+  a.seed = seed; a.env_id_base = env_id_base; a.n = n; a.T = T; a.max_steps = max_steps; a.flags = flags;
+  fill_round_keys(a.round_key, seed, 0u);
+  // one warp per CTA for small batches (4,096 envs then occupy 128 SM sub-partitions), wider CTAs for large ones
+  const int threads = n <= (1 << 15) ? 32 : n <= (1 << 18) ? 64 : 128;
+  const size_t smem = c->world_bytes;
+  void (*kernel)(const StepManyArgs) = all_policy ? step_many_kernel<true> : step_many_kernel<false>;
+  shipenv_ctx::Occ& occ = c->occ_many[(all_policy ? 3 : 0) + (threads == 32 ? 0 : threads == 64 ? 1 : 2)];
+  int grid = 0;
+  if (int rc = grid_for(c, kernel, occ, threads, smem, (n + threads - 1) / threads, &grid)) return rc;
+  kernel<<<grid, threads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
 }
 
 size_t shipenv_step_host_workspace(int64_t n) {
@@ -464,21 +579,37 @@ int shipenv_step_host(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, cons
   const int64_t per = ((n + chunks - 1) / chunks + kGrain - 1) / kGrain * kGrain;
   chunks = int((n + per - 1) / per);
   if (chunks > 1) CUDA_TRY(cudaEventRecord(c->host_fork, user));
-  for (int k = chunks - 1; k >= 0; --k) {            // internal streams first, the caller's stream last
+  // One chunk: enqueue its copy-in, kernel and (with several chunks) its reward copy-out on stream s.
+  auto submit = [&](int k, cudaStream_t s) -> int {
     const int64_t lo = int64_t(k) * per, len = std::min<int64_t>(per, n - lo);
-    cudaStream_t s = k == 0 ? user : c->host_stream[k];
-    if (k > 0) CUDA_TRY(cudaStreamWaitEvent(s, c->host_fork, 0));
     CUDA_TRY(cudaMemcpyAsync(d_act + lo, h_actions + lo, size_t(len) * 2, cudaMemcpyHostToDevice, s));
     shipenv_step_io io{};
     io.reward_f32 = d_reward + lo;
     io.done_bits = d_mask[0] + lo / 32; io.reset_bits = d_mask[1] + lo / 32; io.error_bits = d_mask[2] + lo / 32;
     if (int rc = step_impl(c, ships + lo, clock + lo, d_act + lo, &io, seed, env_id_base + uint64_t(lo), len, max_steps,
-                           flags, 0u, s, 1 + k))
+                           flags & ~SHIPENV_F_CHAINED, 0u, s))
       return rc;
     if (chunks > 1) CUDA_TRY(cudaMemcpyAsync(h_reward + lo, d_reward + lo, size_t(len) * 4, cudaMemcpyDeviceToHost, s));
-    if (k > 0) CUDA_TRY(cudaEventRecord(c->host_join[k], s));
+    return 0;
+  };
+  int rc = 0, forked = 0;                            // internal streams first, the caller's stream last
+  for (int k = chunks - 1; k >= 1 && rc == 0; --k) {
+    cudaStream_t s = c->host_stream[k];
+    if (cudaStreamWaitEvent(s, c->host_fork, 0) != cudaSuccess) { rc = fail(SHIPENV_E_CUDA, "step_host: fork failed"); break; }
+    forked |= 1 << k;
+    rc = submit(k, s);
   }
-  for (int k = 1; k < chunks; ++k) CUDA_TRY(cudaStreamWaitEvent(user, c->host_join[k], 0));
+  if (rc == 0) rc = submit(0, user);
+  // join every internal stream that was given work, also on the error path: the caller's stream stays ordered after
+  // all of it and the fork / join events are free for the next call
+  for (int k = 1; k < chunks; ++k)
+    if (forked & (1 << k)) {
+      if (cudaEventRecord(c->host_join[k], c->host_stream[k]) != cudaSuccess ||
+          cudaStreamWaitEvent(user, c->host_join[k], 0) != cudaSuccess) {
+        if (rc == 0) rc = fail(SHIPENV_E_CUDA, "step_host: join failed");
+      }
+    }
+  if (rc) return rc;
   // Masks: one copy per run of host arrays that are laid out back to back like the device block (each copy costs
   // ~10 us of the copy engine whatever its size).  With one chunk the reward copy is still pending and joins the run.
   struct Span { unsigned char* dst; const unsigned char* src; size_t bytes; };
@@ -621,7 +752,7 @@ int shipenv_rollout(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S,
   RolloutArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, returns,
                 reinterpret_cast<uint4*>(final), steps, status, seed, root_id_base, {}};
   fill_round_keys(a.round_key, seed, kRolloutTweak);
-  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + 8 * 4 * kRolloutThreads;   // world + word FIFO
+  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + RngFifo::kWords * 4 * kRolloutThreads;   // world + word FIFO
   const int64_t tiles = (R * int64_t(S) + kRolloutThreads - 1) / kRolloutThreads;
   int grid = 0;
   if (int rc = grid_for(c, rollout_kernel, c->occ_rollout, kRolloutThreads, smem, tiles, &grid)) return rc;
@@ -644,17 +775,20 @@ int shipenv_mcts(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S, in
   DeviceGuard guard(c->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = sync_world(c, stream)) return rc;
-  double table[SHIPENV_MCTS_MAX_SIMS + 2];
-  table[0] = 0.0;
-  for (int n = 1; n < S + 2; ++n) table[n] = log_table ? log_table[n] : std::log(double(n));
-  CUDA_TRY(cudaMemcpyAsync(c->d_log_table, table, sizeof(double) * (S + 2), cudaMemcpyHostToDevice, stream));
-  MctsArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, c_param, c->d_log_table,
-             action, root_visits, child_action, child_visits, child_total, status, seed, root_id_base, {}};
+  MctsArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, c_param,
+             action, root_visits, child_action, child_visits, child_total, status, seed, root_id_base, {}, {}};
+  // the log table travels in the kernel parameters: nothing of one call can be overwritten by the next
+  a.log_table[0] = 0.0;
+  for (int n = 1; n < S + 2; ++n) a.log_table[n] = log_table ? log_table[n] : std::log(double(n));
   fill_round_keys(a.round_key, seed, kRolloutTweak);
-  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + 8 * 4 * kMctsThreads;   // world + word FIFO
+  // world + word FIFO + log table
+  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + RngFifo::kWords * 4 * kMctsThreads +
+                      sizeof(double) * (SHIPENV_MCTS_MAX_SIMS + 2);
+  const bool small_tree = S + 2 <= 64;               // one node per simulation plus the root
+  void (*kernel)(const MctsArgs) = small_tree ? mcts_kernel<64> : mcts_kernel<128>;
   int grid = 0;
-  if (int rc = grid_for(c, mcts_kernel, c->occ_mcts, kMctsThreads, smem, (R + kMctsThreads - 1) / kMctsThreads, &grid)) return rc;
-  mcts_kernel<<<grid, kMctsThreads, smem, stream>>>(a);
+  if (int rc = grid_for(c, kernel, c->occ_mcts[small_tree ? 0 : 1], kMctsThreads, smem, (R + kMctsThreads - 1) / kMctsThreads, &grid)) return rc;
+  kernel<<<grid, kMctsThreads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   ++g_launches;
   return 0;

@@ -24,6 +24,7 @@ struct StepArgs {
   int obs_bufs;             // observation tiles resident in shared memory (1 or 2)
   uint32_t round_key[20];   // Philox round keys of `seed`: (k0 + r*W0, k1 + r*W1), r = 0..9
   uint32_t* tile_counter;   // step_fast_kernel: global ticket counter (context-owned, zero between launches)
+  uint32_t* chain;          // step_fast_kernel: the env group's chain array (shipenv_step_io.chain) or null
 };
 
 // Observation row head (utils/preprocessing.py:53-60): x, y, fuel, "cargo" (= fuel, the
@@ -40,7 +41,7 @@ __device__ __forceinline__ void track_episode(const shipenv_step_io& io, int i, 
                                               uint32_t clock_before) {
   double* er = io.ep_return;
   if (!er) return;
-  double ep = __dadd_rn(er[i], reward);
+  double ep = __dadd_rn(__ldcg(er + i), reward);   // L2: a chained predecessor on another SM may have written it
   if (was_reset) {
     if (io.stats) {
       double* st = io.stats;
@@ -62,42 +63,65 @@ enum : uint32_t { kFlagDone = 1u, kFlagReset = 2u, kFlagError = 4u };
 // destination re-draw), any word0.  Out of line on purpose: it reloads its inputs and writes
 // every per-env output itself, so nothing of the streaming loop is live across the call and
 // the common case keeps a small register footprint.  Returns kFlag* bits for the ballots.
-__device__ __forceinline__ uint32_t step_general_inline(const StepArgs& a, const void* world_smem, int i) {
-  const WorldView w(world_smem);
-  const uint4 rec = a.ships[i];
-  const uint32_t c = a.clock[i];
-  const int act = (a.flags & SHIPENV_F_ALL_POLICY) ? SHIPENV_ACT_POLICY : int(a.actions[i]);
-  ShipR s = unpack(rec);
+//
+// step_general_core is the transition itself on a ship held in registers (any action, any word0, auto-reset); the
+// kernels differ only in where the ship comes from and where the outputs go.
+struct GeneralOut { double reward; int status, taken; uint32_t flags; };
+
+__device__ __forceinline__ GeneralOut step_general_core(const WorldView& w, const uint32_t* round_key, uint64_t env_id,
+                                                        uint32_t word0, int max_steps, uint32_t step_flags, ShipR& s,
+                                                        uint32_t& c, int act) {
   Rng g;
-  g.seek(a.round_key, c, a.env_id_base + uint64_t(uint32_t(i)), a.word0);
-  double reward = 0.0;
+  g.seek(round_key, c, env_id, word0);
+  GeneralOut o;
+  o.reward = 0.0; o.taken = act; o.flags = 0;
   bool done = false;
-  int taken = act, status;
+  ShipR s1 = s;                        // a rejected action leaves the ship untouched
   if (act == SHIPENV_ACT_POLICY) {
-    taken = -1;
-    status = policy_step(w, s, g, reward, done, taken);
+    o.taken = -1;
+    o.status = policy_step(w, s1, g, o.reward, done, o.taken);
   } else {
     int cat, val;
     decode_action(act, w.h->P, cat, val);
-    status = do_action(w, s, g, cat, val, reward, done);
+    o.status = do_action(w, s1, g, cat, val, o.reward, done);
   }
-  uint32_t flags = 0;
-  if (status == SHIPENV_ST_OK) {
+  if (o.status == SHIPENV_ST_OK) {
     uint32_t c1 = c + 1u;
-    const bool ended = done || (a.max_steps > 0 && int(c1 & 0xFFFFu) >= a.max_steps);
+    const bool ended = done || (max_steps > 0 && int(c1 & 0xFFFFu) >= max_steps);
     bool was_reset = false;
-    if ((a.flags & SHIPENV_F_AUTO_RESET) && ended) {
-      env_reset(w, s, g);  // continues the word stream of this (env, clock) cell
+    if ((step_flags & SHIPENV_F_AUTO_RESET) && ended) {
+      env_reset(w, s1, g);  // continues the word stream of this (env, clock) cell
       c1 = ((c >> 16) + 1u) << 16;
       was_reset = true;
     }
-    track_episode(a.io, i, reward, was_reset, c);
+    s = s1;
+    c = c1;
+    o.flags = (done ? kFlagDone : 0u) | (was_reset ? kFlagReset : 0u);
+  } else {
+    o.reward = 0.0;
+    o.flags = kFlagError;
+  }
+  return o;
+}
+
+__device__ __forceinline__ uint32_t step_general_inline(const StepArgs& a, const void* world_smem, int i) {
+  const WorldView w(world_smem);
+  // read through L2 (ld.global.cg): with chained launches the previous step of this env may have been written by
+  // another SM while this SM's L1 still holds the line from the step before
+  const uint4 rec = __ldcg(a.ships + i);
+  const uint32_t c = __ldcg(a.clock + i);
+  const int act = (a.flags & SHIPENV_F_ALL_POLICY) ? SHIPENV_ACT_POLICY : int(__ldcg(a.actions + i));
+  ShipR s = unpack(rec);
+  uint32_t c1 = c;
+  const GeneralOut o = step_general_core(w, a.round_key, a.env_id_base + uint64_t(uint32_t(i)), a.word0, a.max_steps,
+                                         a.flags, s, c1, act);
+  const double reward = o.reward;
+  const int status = o.status, taken = o.taken;
+  const uint32_t flags = o.flags;
+  if (status == SHIPENV_ST_OK) {
+    track_episode(a.io, i, reward, flags & kFlagReset, c);
     a.ships[i] = pack(s);
     a.clock[i] = c1;
-    flags = (done ? kFlagDone : 0u) | (was_reset ? kFlagReset : 0u);
-  } else {
-    reward = 0.0;
-    flags = kFlagError;
   }
   if (a.io.reward_f32) a.io.reward_f32[i] = float(reward);
   if (a.io.reward_f64) a.io.reward_f64[i] = reward;
@@ -140,6 +164,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_STEP_MIN_BLOCKS) step_kern
   const int n_tiles = (n + kThreads - 1) / kThreads;
   const bool auto_reset = a.flags & SHIPENV_F_AUTO_RESET;
   const bool fast_enabled = a.word0 == 0u && P >= 2;
+  const bool all_policy = a.flags & SHIPENV_F_ALL_POLICY;   // `actions` is not read (and may be null)
 
   // observation tiles: [obs_bufs][kThreads][width] floats after the world blob; the constant
   // port tail of every row is written once, only the 6-float head changes per tile.
@@ -177,10 +202,10 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_STEP_MIN_BLOCKS) step_kern
         const int base = tile * kThreads;
         const int rows8 = min(kThreads, n - base) & ~7;   // whole 16-byte units of every array
         if (rows8 > 0) {
-          mbar_expect_tx(&full_bar[st], uint32_t(rows8) * 22u);
+          mbar_expect_tx(&full_bar[st], uint32_t(rows8) * (all_policy ? 20u : 22u));
           tma_load_bulk(stage[st].ships, a.ships + base, uint32_t(rows8) * 16u, &full_bar[st]);
           tma_load_bulk(stage[st].clock, a.clock + base, uint32_t(rows8) * 4u, &full_bar[st]);
-          tma_load_bulk(stage[st].act, a.actions + base, uint32_t(rows8) * 2u, &full_bar[st]);
+          if (!all_policy) tma_load_bulk(stage[st].act, a.actions + base, uint32_t(rows8) * 2u, &full_bar[st]);
         } else {
           mbar_arrive(&full_bar[st]);
         }
@@ -199,9 +224,11 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_STEP_MIN_BLOCKS) step_kern
     int act = 0;
     mbar_wait(&full_bar[st], uint32_t(it / kStages) & 1u);
     if (tid < (min(kThreads, n - tile * kThreads) & ~7)) {
-      rec = stage[st].ships[tid]; c = stage[st].clock[tid]; act = stage[st].act[tid];
+      rec = stage[st].ships[tid]; c = stage[st].clock[tid];
+      act = all_policy ? SHIPENV_ACT_POLICY : int(stage[st].act[tid]);
     } else if (live) {               // ragged tail of the last tile
-      rec = ld_stream_u4(a.ships + i); c = ld_stream_u32(a.clock + i); act = ld_stream_s16(a.actions + i);
+      rec = ld_stream_u4(a.ships + i); c = ld_stream_u32(a.clock + i);
+      act = all_policy ? SHIPENV_ACT_POLICY : ld_stream_s16(a.actions + i);
     }
     __syncwarp();                    // every lane of this warp has read slot st
     if (lane == 0) mbar_arrive(&empty_bar[st]);
@@ -274,7 +301,7 @@ __global__ void __launch_bounds__(kStepBlock, SHIPENV_STEP_MIN_BLOCKS) step_kern
     if (__any_sync(0xFFFFFFFFu, general)) {
       if (general) {
         flags = step_general(a, smem, i);
-        if (kObs) rec_out = a.ships[i];
+        if (kObs) rec_out = __ldcg(a.ships + i);
       }
     }
     // done / reset / error masks: one ballot word per warp

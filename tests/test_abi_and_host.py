@@ -45,8 +45,8 @@ def test_library_is_sm100a_with_tma():
 def test_struct_layouts_match_header():
     from shippingenv_b200 import _native
     assert ctypes.sizeof(_native.Consts) == 8 + 8 + 11 * 8
-    assert ctypes.sizeof(_native.StepIO) == 10 * 8
-    assert _native.lib().shipenv_abi_version() == 1
+    assert ctypes.sizeof(_native.StepIO) == 11 * 8
+    assert _native.lib().shipenv_abi_version() == 2
 
 
 def test_host_philox_and_port_stock_without_gpu():

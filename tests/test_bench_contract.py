@@ -48,10 +48,13 @@ def test_our_arm_line():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert abs(r["achieved"] * 1e9 - 46 * 2097152 / (d["ms_per_step"] * 1e-3)) / (r["achieved"] * 1e9) < 1e-6
-    assert d["gpu_launches"] == 64 and d["value"] > 1e10
+    assert d["gpu_launches"] == 64 and d["value"] > 1e10 and d["timed_regions"] >= 5
+    assert r["frac_one_stream"] > 0 and r["frac_isolated"] > 0 and d["timing"]["regions"] == d["timed_regions"]
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 2 * 2097152 and e["d2h_bytes_per_step"] > 4 * 2097152 and 0 < e["value"] < d["value"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["python_loop_value_per_core"] > 0
-    assert {"policy_step", "step_with_observation", "mcts_rollouts", "mcts_choose_action", "config_4096_envs"} <= set(d["extras"])
+    assert {"policy_step", "step_with_observation", "mcts_rollouts", "mcts_choose_action", "config_4096_envs",
+            "step_many_2Mi_envs", "dqn_loop"} <= set(d["extras"])
+    assert "error" not in d["extras"]["dqn_loop"] and d["e2e"]["roofline"]["peak"] > 0
