@@ -34,7 +34,7 @@ GROUPS = 4                   # env groups per GPU, stepped round-robin (working 
 ACTION_POOL = 32             # distinct pre-generated action vectors, cycled
 FLUSH_BYTES = 256 << 20      # > 126 MB L2
 METRIC = "env-steps/sec (whole box)"
-CHAINED_ONE_STREAM = False
+CHAINED_ONE_STREAM = True
 
 
 def world():

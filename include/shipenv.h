@@ -90,7 +90,8 @@ enum {
                                      before that previous launch was enqueued (pre-generated action streams, policy
                                      steps).  Ignored, i.e. the launch waits for all earlier work of the stream as usual,
                                      unless the previous launch of this context was a shipenv_step on the same chain
-                                     array and stream that itself took the chain protocol. */
+                                     array and stream, with the same n and output set (i.e. the same kernel and grid),
+                                     that itself took the chain protocol. */
 
 /* One ship, 16 bytes, moved as a single 128-bit load/store.  Mirrors the attributes
  * Environment keeps per ship (shipping/environment.py:37-41). */
@@ -135,11 +136,12 @@ typedef struct {
                               sum return, sum return^2, sum length, episodes, max return, min return */
   uint32_t *chain;         /* NULL, or shipenv_chain_words(n) words of device memory that belong to this (ships, n)
                               pair: zeroed once by the caller, then only touched by shipenv_step.  With it the step
-                              kernels record, per 256-env unit, how many steps have completed, and a launch flagged
-                              SHIPENV_F_CHAINED starts on a tile as soon as the previous launch has finished that tile
-                              instead of waiting for the whole previous grid (consecutive steps of one env group then
-                              overlap at the launch boundary; any other kernel still sees normal stream order).  Every
-                              shipenv_step on these ships must pass the same array (or none of them may be chained). */
+                              kernels split the env range statically over their CTAs and record, per CTA, how many
+                              launches have finished their range; a launch flagged SHIPENV_F_CHAINED lets CTA b start
+                              as soon as CTA b of the previous launch has finished, instead of waiting for the whole
+                              previous grid (consecutive steps of one env group then overlap at the launch boundary;
+                              any other kernel still sees normal stream order).  Every shipenv_step on these ships
+                              must pass the same array (or none of them may be chained). */
 } shipenv_step_io;
 
 typedef struct shipenv_ctx shipenv_ctx;

@@ -102,7 +102,7 @@ class BatchedEnvironment:
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
             self.stats = new_stats(dev)
         self._policy = None
-        # chained launches (include/shipenv.h, shipenv_step_io.chain): per-unit step counters of this env group
+        # chained launches (include/shipenv.h, shipenv_step_io.chain): per-CTA launch counters of this env group
         self._chain = None
         if os.environ.get("SHIPENV_NO_CHAIN") != "1":
             self._chain = torch.zeros(nat.lib().shipenv_chain_words(n), dtype=torch.int32, device=dev)
@@ -166,27 +166,30 @@ class BatchedEnvironment:
         """``Environment.step`` for every env.  ``actions``: int16 [N] flat indices on this device.
 
         ``chained=True`` lets this launch overlap the previous ``step`` of this environment at the launch boundary
-        (``SHIPENV_F_CHAINED``): tile i starts as soon as the previous step has finished tile i, instead of after the
-        whole previous grid.  Only for ``actions`` that were complete before the previous step was enqueued
+        (``SHIPENV_F_CHAINED``): CTA b starts as soon as CTA b of the previous chained step has finished its share of
+        the envs, instead of after the whole previous grid.  Only for ``actions`` that were complete before the previous step was enqueued
         (pre-generated action streams); policy steps (``step_policy``) are always chained, they read no actions.
         Results are identical either way."""
         if actions.dtype != torch.int16 or actions.device != self.device or actions.numel() != self.n:
             raise ValueError("actions must be an int16 tensor of shape [num_envs] on the env's device")
         if not actions.is_contiguous():
             actions = actions.contiguous()
-        key = (want_obs, want_status, want_taken, want_reward64, None if obs_out is None else obs_out.data_ptr())
+        # the chain array travels only with launches that ask for it: every other step keeps the ticket-scheduled grid
+        use_chain = (chained or actions is self._policy) and self._chain is not None
+        key = (want_obs, want_status, want_taken, want_reward64, None if obs_out is None else obs_out.data_ptr(),
+               use_chain)
         cached = self._step_cache.get(key)
         if cached is None:
             if len(self._step_cache) >= 64:        # a caller cycling through many obs_out buffers: start over
                 self._step_cache.clear()
                 self._io_keepalive.clear()
             cached = self._step_cache[key] = self._build_step_io(want_obs, want_status, want_taken, want_reward64,
-                                                                 obs_out)
+                                                                 obs_out, use_chain)
         io_ref, res = cached
         flags = (nat.F_AUTO_RESET if self.auto_reset else 0) | (nat.F_ALL_POLICY if actions is self._policy else 0)
-        if (chained or actions is self._policy) and self._chain_ok:
-            flags |= nat.F_CHAINED         # the library honours it only right behind another step of this env
-        self._chain_ok = True
+        if use_chain and self._chain_ok:
+            flags |= nat.F_CHAINED         # the library honours it only right behind another chained step of this env
+        self._chain_ok = use_chain
         rc = self._lib_step(self._ctx_handle, self._ships_ptr, self._clock_ptr, actions.data_ptr(), io_ref, self.seed,
                             self.env_id_base, self.n, self.max_steps, flags,
                             word0, self._stream())
@@ -194,7 +197,7 @@ class BatchedEnvironment:
             nat.check(rc)
         return res
 
-    def _build_step_io(self, want_obs, want_status, want_taken, want_reward64, obs_out):
+    def _build_step_io(self, want_obs, want_status, want_taken, want_reward64, obs_out, use_chain=False):
         import ctypes
         io = nat.StepIO()
         io.reward_f32 = self.reward.data_ptr()
@@ -218,7 +221,7 @@ class BatchedEnvironment:
             io.obs = res.obs.data_ptr()
         if self.ep_return is not None:
             io.ep_return, io.stats = self.ep_return.data_ptr(), self.stats.data_ptr()
-        if self._chain is not None:
+        if use_chain:
             io.chain = self._chain.data_ptr()
         self._io_keepalive.append(io)
         return ctypes.byref(io), res

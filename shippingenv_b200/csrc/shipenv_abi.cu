@@ -83,6 +83,8 @@ struct shipenv_ctx {
   uint32_t* last_chain = nullptr;
   cudaStream_t last_chain_stream = nullptr;
   bool last_chain_capturing = false;
+  int last_chain_grid = 0;              // its grid size and env count: a chained launch continues the same static split
+  int64_t last_chain_n = 0;
   // the world upload: other streams wait for it until it has completed
   cudaEvent_t world_event = nullptr;
   cudaStream_t world_stream = nullptr;
@@ -435,15 +437,20 @@ static int step_impl(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const
     a.chain = a.io.chain;
     if (a.chain) {
       if (reinterpret_cast<uintptr_t>(a.chain) & 7u) return fail(SHIPENV_E_ARG, "step: chain must be 8-byte aligned");
-      // SHIPENV_F_CHAINED is honoured only directly behind a chain-protocol launch on the same array and stream
-      // (and not across the end of a stream capture); otherwise this launch waits for everything before it
+      // SHIPENV_F_CHAINED is honoured only directly behind a chain-protocol launch on the same array and stream with
+      // the same grid size and env count (CTA b continues CTA b's static range), and not across the end of a stream
+      // capture; otherwise this launch waits for everything before it
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(stream, &cap);
       const bool capturing = cap != cudaStreamCaptureStatusNone;
-      if (!(prev_chain == a.chain && prev_chain_stream == stream && prev_chain_capturing == capturing))
+      if (grid > kChainMaxCtas) return fail(SHIPENV_E_ARG, "step: chain arrays serve grids of up to %d CTAs", kChainMaxCtas);
+      if (!(prev_chain == a.chain && prev_chain_stream == stream && prev_chain_capturing == capturing &&
+            c->last_chain_grid == grid && c->last_chain_n == n))
         a.flags &= ~SHIPENV_F_CHAINED;
       c->last_chain = a.chain;
       c->last_chain_capturing = capturing;
+      c->last_chain_grid = grid;
+      c->last_chain_n = n;
     } else {
       a.flags &= ~SHIPENV_F_CHAINED;
     }
@@ -490,9 +497,19 @@ int shipenv_step(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int
                    static_cast<cudaStream_t>(stream_));
 }
 
+#ifdef SHIPENV_TRACE
+// tuning builds only: per-CTA timeline records of step_fast_kernel go to `buf` (8 x u64 each); null switches it off
+int shipenv_debug_trace(void* buf) {
+  unsigned int zero = 0;
+  if (cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf)) != cudaSuccess) return SHIPENV_E_CUDA;
+  if (cudaMemcpyToSymbol(g_trace_count, &zero, sizeof(zero)) != cudaSuccess) return SHIPENV_E_CUDA;
+  return 0;
+}
+#endif
+
 size_t shipenv_chain_words(int64_t n) {
   if (n <= 0) return 0;
-  return size_t(kChainEpoch) + size_t((n + kChainUnit - 1) / kChainUnit) + 1;
+  return size_t(kChainDone) + size_t(kChainMaxCtas);
 }
 
 int shipenv_step_many(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, const int16_t* actions, int T,

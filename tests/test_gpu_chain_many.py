@@ -91,9 +91,9 @@ def test_bench_kernel_at_bench_size_vs_oracle(torch_cuda, default_map):
 @pytest.mark.parametrize("n,max_steps,policy", [(1 << 20, 7, False), (300_001, 3, False), (4096, 11, False),
                                                 (777, 5, False), (1 << 19, 9, True), (70_001, 4, True)])
 def test_chained_launches_match_oracle(torch_cuda, default_map, n, max_steps, policy):
-    """T steps enqueued back to back with SHIPENV_F_CHAINED (each launch starts on a tile as soon as the previous
-    launch has finished that tile): the final state and the last step's outputs equal the oracle's after T steps.
-    Short episodes keep the deferred general path (and its late tile publication) busy in every launch."""
+    """T steps enqueued back to back with SHIPENV_F_CHAINED (CTA b of each launch starts as soon as CTA b of the previous
+    launch has finished its static env range): the final state and the last step's outputs equal the oracle's after T steps.
+    Short episodes keep the deferred general path busy in every launch."""
     torch = torch_cuda
     from shippingenv_b200 import BatchedEnvironment
     seed, T = 4242, 24
@@ -121,11 +121,14 @@ def test_chained_launches_match_oracle(torch_cuda, default_map, n, max_steps, po
     assert (bits(r.done_bits, n) == want["done"].astype(bool)).all()
     assert (bits(r.reset_bits, n) == want["reset"].astype(bool)).all()
     assert (bits(r.error_bits, n) == (want["status"] != 0)).all()
-    # the chain array is quiescent: every 256-env unit has been completed T times by 8 warps
+    # the chain array is quiescent: every CTA of the grid has arrived at and finished T launches
     chain = env._chain.cpu().numpy().view(np.uint32)
-    units = (n + 255) // 256
-    assert chain[0] == 0 and chain[1] == T          # arrivals of the current launch | launches so far
-    assert (chain[320:320 + units] == 8 * T).all()
+    word = int(chain[0]) | int(chain[1]) << 32       # CTAs of all launches so far << 16 | arrivals of the current one
+    done = chain[32:]
+    grid = int((done != 0).sum())
+    assert 1 <= grid <= (n + 511) // 512
+    assert word == (T * grid) << 16
+    assert (done[:grid] == T * grid).all() and (done[grid:] == 0).all()
     # mixing in other launches (observation variant, general kernel via word0, unchained steps) keeps it consistent
     env.step(acts[0], want_obs=True); ref.step(a_np[0])
     env.step(acts[1], chained=True); ref.step(a_np[1])
