@@ -88,6 +88,32 @@ __device__ __forceinline__ unsigned int trace_smid() {
 #define SHIPENV_TRACE_SET(slot, value) do { } while (0)
 #endif
 
+// Episode end with auto-reset behind a straight-line move (:227-243): the terminal record and clock + 1 have been
+// stored; draw the new episode from the words of the (env, clock) cell behind the move's draws -- explicit move:
+// words 0, 1 -> 2..; policy: 0, 1, 2 -> 3.. -- as env_reset (transition.cuh) does, and overwrite record and clock.
+template <bool kPolicy>
+__device__ __forceinline__ uint4 reset_in_place(const StepArgs& a, const WorldView& w, int i, uint32_t c) {
+  const uint64_t id = a.env_id_base + uint64_t(uint32_t(i));
+  const uint32_t P = uint32_t(w.h->P);               // >= 2 with auto-reset (checked on the host)
+  uint32_t wd[4];
+  philox_rk(0u, c, uint32_t(id), uint32_t(id >> 32), a.round_key, wd);
+  const uint32_t ro = __umulhi(kPolicy ? wd[3] : wd[2], P);                        // randint(0, P-1), :232
+  uint32_t rd = kPolicy ? ro : __umulhi(wd[3], P);                                  // :233 (policy: word 4)
+  for (uint32_t blk = 1u; rd == ro; ++blk) {         // `while dest == origin` (:236-237): further words of the cell
+    philox_rk(blk, c, uint32_t(id), uint32_t(id >> 32), a.round_key, wd);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (rd == ro) rd = __umulhi(wd[k], P);
+  }
+  uint4 fresh;
+  fresh.x = (w.h->port[ro] & 0xFFFFu) | (ro << 16) | (rd << 24);
+  fresh.y = uint32_t(w.h->cargo0);
+  fresh.z = uint32_t(__double2loint(w.h->fuel0)); fresh.w = uint32_t(__double2hiint(w.h->fuel0));
+  st_stream_u4(a.ships + i, fresh);
+  a.clock[i] = ((c >> 16) + 1u) << 16;
+  return fresh;
+}
+
 // kEpt envs per thread: a tile is 256 * kEpt envs; thread t owns envs t, t + 256, ... of the tile.  Two
 // independent env chains per thread interleave (ILP) and share the per-tile bookkeeping.
 template <int kEpt>
@@ -274,6 +300,7 @@ __global__ void __launch_bounds__(kFastBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       uint4 rec_e[kEpt];
       uint32_t c_e[kEpt];
       int act_e[kEpt];
+      bool reset_e[kEpt];
 #pragma unroll
       for (int e = 0; e < kEpt; ++e) {
         rec_e[e] = lds_u4(my_ship + so + uint32_t(e) * kThreads * 16u);
@@ -329,17 +356,16 @@ __global__ void __launch_bounds__(kFastBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
       const bool trigger = w_loss <= lds_u32(wb + uint32_t(offsetof(WorldHdr, loss_thr)) + min(uint32_t(rec.y), cap) * 4u);  // :318-320
       const bool arrive = pos1 == (pd & 0xFFFFu);                                         // :325
       const uint32_t c1 = c + 1u;
-      // An episode end with auto-reset (once per few hundred steps of an env) goes the general way too: the reset
-      // draws, the record and clock rewrite and their predicated selects would otherwise ride along on every step.
+      // An episode end with auto-reset comes once per few hundred steps of an env.  The step itself is the plain move
+      // (the terminal record is stored like any other); the new episode is drawn behind a warp-uniform branch after
+      // the stores (taken by one warp-step in ten), by the same code the general path uses, and overwrites record
+      // and clock.  Nothing of it rides along on the other steps, and no env waits on the deferred list for it.
       const bool do_reset = auto_reset && (no_fuel || (c1 & 0xFFFFu) >= trunc_at);
-      // (the fused-observation variant resolves general lanes on the spot, a whole warp waiting for them, so it keeps
-      // the reset in line: words 2 and 3 are the two port draws, :232-233; equal draws need more words)
-      const uint32_t ro = kObs ? __umulhi(wd[2], uint32_t(w.h->P)) : 0u, rd = kObs ? __umulhi(wd[3], uint32_t(w.h->P)) : 0u;
-      const bool reset_general = (kObs && !kPolicy) ? (do_reset && ro == rd) : do_reset;
-      // policy: an off-map choice is re-drawn -- the general way as well
-      const bool general = kPolicy ? (!is_move || !in_map || trigger || arrive || do_reset)
-                                   : (!is_move || (in_map && (trigger || arrive || reset_general)));
+      // policy: an off-map choice is re-drawn -- the general way
+      const bool general = kPolicy ? (!is_move || !in_map || trigger || arrive)
+                                   : (!is_move || (in_map && (trigger || arrive)));
       const bool ok = is_move && in_map && !general;
+      const bool reset_here = ok && do_reset;
       const bool off_map = !kPolicy && is_move && !in_map;
       const uint32_t ridx = (no_fuel ? 4u : 0u) | ((wbit ^ 1u) << 1) | closer_bit;        // index of move_reward[]
       {
@@ -348,17 +374,10 @@ __global__ void __launch_bounds__(kFastBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         out.x = (rec.x & 0xFFFF0000u) | pos1;
         out.y = rec.y;
         out.z = uint32_t(__double2loint(fuel1)); out.w = uint32_t(__double2hiint(fuel1));
-        uint32_t c_out = c1;
-        if (kObs && !kPolicy && do_reset) {                                                // :227-243
-          out.x = (lds_u32(wb + uint32_t(offsetof(WorldHdr, port)) + ro * 4u) & 0xFFFFu) | (ro << 16) | (rd << 24);
-          out.y = uint32_t(w.h->cargo0);
-          out.z = uint32_t(__double2loint(w.h->fuel0)); out.w = uint32_t(__double2hiint(w.h->fuel0));
-          c_out = ((c >> 16) + 1u) << 16;
-        }
         const float r = lds_f32(wb + uint32_t(offsetof(WorldHdr, move_reward_f32)) + ridx * 4u);
         if (ok) {
           st_stream_u4(a.ships + i, out);
-          a.clock[i] = c_out;
+          a.clock[i] = c1;
         }
         if (!general && (kLean || a.io.reward_f32)) a.io.reward_f32[i] = ok ? r : 0.f;
         if (!kLean) {
@@ -367,10 +386,17 @@ __global__ void __launch_bounds__(kFastBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
             if (a.io.reward_f64) a.io.reward_f64[i] = r64;
             if (a.io.status) a.io.status[i] = uint8_t(ok ? SHIPENV_ST_OK : SHIPENV_ST_OFF_MAP);
             if (a.io.taken) a.io.taken[i] = int16_t(kPolicy ? m : act);
-            if (ok) track_episode(a.io, i, r64, kObs && !kPolicy && do_reset, c);
+            if (ok) track_episode(a.io, i, r64, reset_here, c);
           }
         }
         if (kObs) fin = ok ? out : rec;
+      }
+      if (kObs) {                    // the observation row needs the new episode now
+        if (__any_sync(0xFFFFFFFFu, reset_here)) {
+          if (reset_here) fin = reset_in_place<kPolicy>(a, w, i, c);
+        }
+      } else {
+        reset_e[e] = reset_here;     // behind both envs' straight-line code, which stays interleaved
       }
       const uint32_t gen_w = __ballot_sync(0xFFFFFFFFu, general);
       uint32_t gflags = 0;
@@ -384,8 +410,7 @@ __global__ void __launch_bounds__(kFastBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         n_defer += __popc(gen_w);
       }
       const uint32_t done_w = __ballot_sync(0xFFFFFFFFu, (ok && no_fuel) || (gflags & kFlagDone));
-      const uint32_t reset_w = kObs ? __ballot_sync(0xFFFFFFFFu, (!kPolicy && ok && do_reset) || (gflags & kFlagReset))
-                                    : 0u;                          // without observations resets are general-path work
+      const uint32_t reset_w = __ballot_sync(0xFFFFFFFFu, reset_here || (gflags & kFlagReset));
       const uint32_t err_w = __ballot_sync(0xFFFFFFFFu, off_map || (gflags & kFlagError));
       {
         const uint32_t mask_v = lane == 0 ? done_w : lane == 1 ? reset_w : err_w;
@@ -407,6 +432,16 @@ __global__ void __launch_bounds__(kFastBlock, SHIPENV_FAST_MIN_BLOCKS) step_fast
         consumer_sync();
       }
       }  // envs of this thread
+      if (!kObs) {
+        bool any_reset = false;
+#pragma unroll
+        for (int e = 0; e < kEpt; ++e) any_reset |= reset_e[e];
+        if (__any_sync(0xFFFFFFFFu, any_reset)) {
+#pragma unroll
+          for (int e = 0; e < kEpt; ++e)
+            if (reset_e[e]) reset_in_place<kPolicy>(a, w, tile * kTile + e * kThreads + tid, c_e[e]);
+        }
+      }
     }
     // ------------------------------ drain the deferred envs, a warp-full at a time ------------------------------
     if (n_defer == 0 && !more) break;
