@@ -344,7 +344,7 @@ def run_ours(args):
         for t in range(count):
             envs[t % G].step(pool[t % ACTION_POOL], chained=chained)
 
-    def capture(multi_stream, chained=False):
+    def capture(multi_stream, chained=False, count=None):
         for g in range(G):
             envs[g].use_stream(gstreams[g] if multi_stream else None)
         torch.cuda.synchronize(dev)
@@ -354,7 +354,7 @@ def run_ours(args):
             if multi_stream:
                 for st in gstreams:
                     st.wait_stream(cur)
-            issue_steps(K, chained)
+            issue_steps(K if count is None else count, chained)
             if multi_stream:
                 for st in gstreams:
                     cur.wait_stream(st)
@@ -393,13 +393,15 @@ def run_ours(args):
     resets = int(sum(int(unpack_bits(e.reset_bits, n).sum().item()) for e in envs))
 
     # ---- the same K launches on ONE stream (strictly in stream order), reported separately ----
+    # (a chain starts with one unchained launch per group: regions of at least 256 launches, reported per launch)
+    Ko = max(K, 256)
     try:
-        graph_one = capture(False, chained=args.chained)
+        graph_one = capture(False, chained=args.chained, count=Ko)
         issue_one = graph_one.replay
     except Exception:
         def issue_one():
-            issue_steps(K, args.chained)
-    one_ms = median(timed_regions(torch, dev, issue_one, K, barrier=barrier))
+            issue_steps(Ko, args.chained)
+    one_ms = median(timed_regions(torch, dev, issue_one, Ko, barrier=barrier)) * K / Ko
 
     # ---- single group, L2 flushed by a 256 MiB fill between steps, one event pair per step: the isolated launch ----
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -495,11 +497,12 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         algo = n * BYTES_PER_STEP
         achieved = algo / (kernel_ms * 1e-3) / 1e9
-        traffic, traffic_src = None, None
+        traffic, traffic_src, ncu_us = None, None, None
         prof = os.path.join(ROOT, "profiles", "r2_step_kernel_traffic.json")
         if os.path.exists(prof):
             pj = json.load(open(prof))
             traffic, traffic_src = pj.get("dram_bytes_per_launch"), pj.get("how")
+            ncu_us = pj.get("ncu_us_per_launch_serialised")
         e2e_bytes = 2 * n + 4 * n + 12 * nw
         e2e_value = n_total * Ke / (e2e_ms * 1e-3)
         link_total = rates.tolist()
@@ -526,8 +529,12 @@ def run_ours(args):
                          "how": "algorithmic bytes / (median region time / K); launches of independent env groups sit "
                                 "on different streams and overlap at their boundaries",
                          "frac_one_stream": algo / (one_ms / K * 1e-3) / 1e9 / peak,
-                         "one_stream_how": "the same K launches in one stream, groups round-robin"
+                         "one_stream_how": f"max(K, 256) = {max(K, 256)} launches in ONE stream, groups round-robin"
                                            + (", SHIPENV_F_CHAINED (pre-generated actions)" if args.chained else ""),
+                         "traffic_over_algorithmic": traffic / algo if traffic else None,
+                         "frac_ncu_serialised": algo / (ncu_us * 1e-6) / 1e9 / peak if ncu_us else None,
+                         "ncu_serialised_how": "mean gpu__time_duration of the same capture (kernels serialised by the "
+                                               "profiler: every launch pays its own ramp and tail)",
                          "frac_isolated": algo / (isolated_ms * 1e-3) / 1e9 / peak,
                          "isolated_how": "one launch alone between CUDA events, L2 flushed by a 256 MiB fill before it "
                                          "(median of per-launch times): ramp and tail fully exposed"},
