@@ -285,6 +285,12 @@ def main():
     passable = port_meta(b)["passable"].astype(bool)
     acts = np.zeros((T, N), np.int64)
     tr_parts = []
+    # G12: the reference's own grid paint (np_game: BOAT on the ship, TRAVEL behind it, PORT cells painted over;
+    # shipping/environment.py:228, 240, 303-304) of a few of these envs after reset and after every step
+    paint_envs = [0, 3, 9, 30]
+    frames = np.zeros((T + 1, len(paint_envs), 100, 100), np.uint8)
+    for k, i in enumerate(paint_envs):
+        frames[0, k] = b.envs[i].np_game
     for t in range(T):
         row = np.zeros(N, np.int64)
         for i, e in enumerate(b.envs):
@@ -299,6 +305,8 @@ def main():
                 row[i] = k if k is not None and (t * 7 + i) % 11 else int(rng.integers(0, 4))
         acts[t] = row
         tr_parts.append(run(b, row[None, :], 0, False))
+        for k, i in enumerate(paint_envs):
+            frames[t + 1, k] = b.envs[i].np_game
     tr = {k: np.concatenate([p[k] for p in tr_parts]) for k in
           ("actions", "pos", "cargo", "fuel", "reward", "done", "status", "reset", "taken", "clock")}
     for k in ("init_pos", "init_cargo", "init_fuel", "init_clock", "max_steps", "auto_reset",
@@ -307,6 +315,11 @@ def main():
     print("  navigator: arrivals =", int((tr["reward"] > 5).sum()), " dones =", int(tr["done"].sum()),
           " min fuel =", np.frombuffer(tr["fuel"][-1].tobytes(), np.float64).min())
     save("g4_navigator", **tr, **port_meta(b))
+    # stored as the frame after reset plus the cells each step changed: (step, env slot, x, y, new value)
+    changed = [(t, k, x, y, frames[t + 1, k, x, y]) for t in range(T) for k in range(len(paint_envs))
+               for x, y in zip(*np.nonzero(frames[t + 1, k] != frames[t, k]))]
+    save("g12_paint", env_index=np.array(paint_envs, np.int64), frame0=frames[0],
+         changes=np.array(changed, np.int32).reshape(-1, 5))
 
     # --- G5: all-water synthetic map: edges, off-map rejections, 2 ports --------------
     import cv2

@@ -1,6 +1,9 @@
 """Subprocess body of tests/test_reference_agents_cpu.py: the reference's agents, unmodified, on the facade.
 
     PYTHONPATH=<repo>/compat:<repo>:<repo>/tests:/root/reference python tests/run_reference_agents.py
+
+SHIPENV_AGENTS_ON=cuda runs them on the real kernels (tests/test_gpu_facade.py, where a reference checkout exists:
+$SHIPPINGENV_REF or /root/reference); otherwise the facade's launches are computed by the oracle.
 """
 import json
 import os
@@ -11,8 +14,12 @@ import types
 for name in ("matplotlib", "matplotlib.pyplot"):          # agents/sarsa.py imports pyplot; not installed here
     sys.modules.setdefault(name, types.ModuleType(name))
 
-import facade_on_oracle
-contexts = facade_on_oracle.install()
+REF = os.environ.get("SHIPPINGENV_REF", "/root/reference")
+ON_CUDA = os.environ.get("SHIPENV_AGENTS_ON") == "cuda"    # tests/test_gpu_facade.py: the real kernels
+contexts = {}
+if not ON_CUDA:
+    import facade_on_oracle
+    contexts = facade_on_oracle.install()
 
 import shipping                                            # compat/shipping: the drop-in
 assert "compat" in shipping.__file__, shipping.__file__
@@ -21,10 +28,10 @@ from agents.mcts import MCTSAgent                          # /root/reference/age
 from agents.sarsa import SARSAAgent
 from agents.dqn import DQNAgent
 import agents
-assert agents.__file__.startswith("/root/reference/"), agents.__file__
+assert agents.__file__.startswith(REF.rstrip("/") + "/"), agents.__file__
 from utils.constants import DEFAULT_PORTS
 
-os.chdir("/root/reference")                                # MCTSAgent re-opens "mapa_mundi_binario.jpg" by relative path
+os.chdir(REF)                                # MCTSAgent re-opens "mapa_mundi_binario.jpg" by relative path
 random.seed(7)
 out = {}
 
@@ -66,5 +73,9 @@ agent = DQNAgent(env)
 res = agent.train(episodes=3, render=False, verbose=False, max_steps=40, max_total_steps=100)
 s = res.get_summary()
 out["dqn"] = {"episodes": s["total_episodes"], "mean_reward": s["mean_reward"]}
-out["launches"] = sum(c[0].launches for c in contexts.values())
+if ON_CUDA:
+    from shippingenv_b200 import launch_count
+    out["launches"] = launch_count()
+else:
+    out["launches"] = sum(c[0].launches for c in contexts.values())
 print("RESULT " + json.dumps(out))

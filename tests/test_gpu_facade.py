@@ -98,6 +98,13 @@ def test_facade_replays_navigator_trace():
             assert env._clock == z["clock"][t, i]
 
 
+def test_facade_paints_np_game_like_the_reference():
+    """g12: the reference's np_game (BOAT / TRAVEL paint, port cells painted over, reset wiping the trail) after reset
+    and after each of the 700 navigator steps of four envs, compared cell by cell."""
+    from paint_trace import replay_paint_trace
+    assert replay_paint_trace() == 4 * 700
+
+
 def test_facade_crafted_states_and_policy_loop():
     """g6: attributes assigned from outside (as agents/mcts.py:199-208 does), then the reference's
     `a = sample_action(); try: step(a) except: continue` loop for policy rows."""
@@ -247,3 +254,28 @@ def test_facade_mcts_extensions_match_batched_kernels():
         rets = env.rollout_returns(6, 25, root_id=1000)
         assert len(rets) == 6 and len(set(rets)) > 1
         assert before == (list(env.ship_position), env.fuel, env.cargo, env._clock)   # planning never moves the env
+
+
+REF = os.environ.get("SHIPPINGENV_REF", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "agents")),
+                    reason="no reference checkout on this box ($SHIPPINGENV_REF or /root/reference)")
+def test_unmodified_reference_agents_on_the_cuda_facade():
+    """The reference's agents/mcts.py, agents/sarsa.py and agents/dqn.py, unmodified, import ``shipping`` from compat/
+    and train on the drop-in facade with every launch on the GPU (the CPU suite runs the same script with the launches
+    computed by the oracle).  Runs wherever a reference checkout travels with the GPU."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "compat"), ROOT, os.path.join(ROOT, "tests"), REF])
+    env["SHIPENV_AGENTS_ON"] = "cuda"
+    env["SHIPPINGENV_REF"] = REF
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_agents.py")], capture_output=True,
+                         text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    assert r["mcts"]["episodes"] >= 1 and r["sarsa"]["episodes"] >= 1 and r["dqn"]["episodes"] >= 1
+    assert r["sarsa"]["q_entries"] > 10 and r["launches"] > 500
