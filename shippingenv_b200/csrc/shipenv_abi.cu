@@ -535,13 +535,18 @@ int shipenv_step_many(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, cons
   a.status = status; a.taken = taken; a.reward_f64 = reward_f64;
   a.seed = seed; a.env_id_base = env_id_base; a.n = n; a.T = T; a.max_steps = max_steps; a.flags = flags;
   fill_round_keys(a.round_key, seed, 0u);
-  // one warp per CTA for small batches (4,096 envs then occupy 128 SM sub-partitions), wider CTAs for large ones
+  // one warp per CTA and one env per thread for small batches (4,096 envs then occupy 128 SMs), wider CTAs with two
+  // interleaved envs per thread for large ones
   const int threads = n <= (1 << 15) ? 32 : n <= (1 << 18) ? 64 : 128;
+  // (the random policy sends a twentieth of its steps the general way -- off-map re-draws, port pick-ups --, which
+  // a second env per thread would only serialise further)
+  const int ept = (threads == 128 && !all_policy) ? 2 : 1;
   const size_t smem = c->world_bytes;
-  void (*kernel)(const StepManyArgs) = all_policy ? step_many_kernel<true> : step_many_kernel<false>;
+  void (*kernel)(const StepManyArgs) = ept == 2 ? step_many_kernel<false, 2>
+                                       : all_policy ? step_many_kernel<true, 1> : step_many_kernel<false, 1>;
   shipenv_ctx::Occ& occ = c->occ_many[(all_policy ? 3 : 0) + (threads == 32 ? 0 : threads == 64 ? 1 : 2)];
   int grid = 0;
-  if (int rc = grid_for(c, kernel, occ, threads, smem, (n + threads - 1) / threads, &grid)) return rc;
+  if (int rc = grid_for(c, kernel, occ, threads, smem, (n + int64_t(threads) * ept - 1) / (int64_t(threads) * ept), &grid)) return rc;
   kernel<<<grid, threads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   ++g_launches;
