@@ -454,23 +454,13 @@ def run_ours(args):
     # ---- episode statistics: the one collective of the path (NCCL all-reduce of 6 doubles), checked against a gather
     stats_check = None
     if world_size > 1:
-        from shippingenv_b200.stats import reduce_stats, summarize
+        from shippingenv_b200.stats import crosscheck
         tracked = BatchedEnvironment(1 << 16, passable=world(), seed=SEED, device=dev, env_id_base=rank << 16,
                                      max_steps=40, auto_reset=True, track_stats=True)
         tracked.reset()
         for t in range(64):
             tracked.step(pool[t % ACTION_POOL][:1 << 16].contiguous())
-        summary = tracked.episode_summary()                 # all-reduce over NCCL
-        every = [torch.zeros_like(tracked.stats) for _ in range(world_size)]
-        dist.all_gather(every, tracked.stats)               # the same numbers gathered rank by rank
-        st = torch.stack(every).cpu().numpy()
-        want = dict(episodes=float(st[:, 3].sum()), sum_return=float(st[:, 0].sum()), best=float(st[:, 4].max()),
-                    worst=float(st[:, 5].min()))
-        red = reduce_stats(tracked.stats).cpu().numpy()
-        stats_check = {"episodes": summary["total_episodes"], "mean_return": summary["mean_return"],
-                       "nccl_equals_gathered": bool(red[3] == want["episodes"] and red[4] == want["best"]
-                                                    and red[5] == want["worst"]
-                                                    and abs(red[0] - want["sum_return"]) <= 1e-9 * abs(want["sum_return"]))}
+        stats_check = crosscheck(tracked.stats)             # all-reduce over NCCL vs all-gather + host sum
 
     # ---- the other device paths of the scope table, N = 1 only, a few launches each (reported as extras) ----
     extras = {}

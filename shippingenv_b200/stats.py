@@ -47,3 +47,24 @@ def summarize(stats):
     var = max(s[1] / n - mean * mean, 0.0)
     return {"total_episodes": int(n), "mean_reward": mean, "std_reward": math.sqrt(var), "max_reward": s[4],
             "min_reward": s[5], "mean_length": s[2] / n, "total_steps": int(s[2])}
+
+
+def crosscheck(stats, group=None):
+    """The all-reduced statistics next to the same numbers gathered rank by rank and summed on the host (bench.py and
+    the gloo test use it to show that the one collective of the path computes what it should)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    red = reduce_stats(stats, group)
+    if world > 1:
+        every = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(every, stats, group=group)
+        st = torch.stack(every).cpu()
+    else:
+        st = stats.detach().cpu()[None]
+    want = torch.cat([st[:, :4].sum(0), st[:, 4:5].max(0).values, st[:, 5:6].min(0).values])
+    r = red.detach().cpu()
+    same = bool(r[3] == want[3] and r[4] == want[4] and r[5] == want[5] and r[2] == want[2]
+                and abs(float(r[0] - want[0])) <= 1e-9 * max(1.0, abs(float(want[0]))))
+    summary = summarize(red)
+    return {"episodes": summary["total_episodes"], "mean_reward": summary["mean_reward"],
+            "mean_length": summary["mean_length"], "reduced_equals_gathered": same}

@@ -22,7 +22,7 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from shippingenv_b200.stats import new_stats, reduce_stats, shard_range, summarize
+    from shippingenv_b200.stats import crosscheck, new_stats, reduce_stats, shard_range, summarize
     lo, hi = shard_range(10, rank, world)
     # episode returns owned by this rank: env id e contributes return e - 4.5, length 100 + e
     st = new_stats("cpu")
@@ -31,8 +31,9 @@ def _worker(rank, world, port, out):
         st[0] += r; st[1] += r * r; st[2] += 100 + e; st[3] += 1
         st[4] = max(st[4].item(), r); st[5] = min(st[5].item(), r)
     red = reduce_stats(st)
+    check = crosscheck(st)                 # what bench.py prints at N > 1: all-reduce next to all-gather + host sum
     if rank == 0:
-        torch.save({"summary": summarize(red), "local": summarize(st), "range": (lo, hi)}, out)
+        torch.save({"summary": summarize(red), "local": summarize(st), "range": (lo, hi), "check": check}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -47,6 +48,8 @@ def test_stats_allreduce_world2(tmp_path):
     assert s["max_reward"] == 4.5 and s["min_reward"] == -4.5 and abs(s["mean_reward"]) < 1e-12
     assert abs(s["std_reward"] - (sum((e - 4.5) ** 2 for e in range(10)) / 10) ** 0.5) < 1e-12
     assert s["mean_length"] == 104.5
+    assert res["check"] == {"episodes": 10, "mean_reward": s["mean_reward"], "mean_length": 104.5,
+                            "reduced_equals_gathered": True}
 
 
 def test_reduce_without_process_group_is_identity():
