@@ -290,6 +290,42 @@ int shipenv_host_device_pointer(void *host_ptr, void **device_ptr);
  * Python values, like shipping/environment.py:376, so it has to wait).  Nothing else in this ABI synchronises. */
 int shipenv_stream_synchronize(shipenv_ctx *ctx, void *stream);
 
+/* The N = 1 step without a launch per call: Environment.step (shipping/environment.py:359-376) followed by the draw of
+ * the sample_action call that usually comes next (:245-263), exactly what shipenv_step_sample computes for n = 1, served
+ * by a resident one-warp kernel that polls a page-locked mailbox owned by the context.  The call writes the request
+ * (ship, clock, action, word0, seed, env id, max_steps, flags -- the server keeps no env state, so any number of
+ * Environment objects share it), spins until the kernel has answered and copies the answer into `block`; no launch and
+ * no stream synchronisation on the way (~6 us instead of ~23 us per step).  The kernel retires by itself after
+ * `idle_us` without a request (default 2000; a device-wide synchronisation elsewhere in the process waits at most that
+ * long) and is launched again by the next call; it is restarted when the world of the context has changed.
+ * `block` is HOST memory (it need not be page-locked) laid out like shipenv_host_block.  Returns 0 also when the step
+ * was rejected (block->status says why, nothing changed). */
+typedef struct shipenv_host_block {
+  shipenv_ship ship;        /*   0  in: the ship; out: the ship after the step */
+  double reward;            /*  16  out */
+  uint8_t pad0[8];
+  uint32_t clock;           /*  32  in / out */
+  uint8_t pad1[12];
+  int16_t action;           /*  48  in: flat action index */
+  uint8_t pad2[14];
+  uint32_t done_bits, reset_bits, error_bits;   /* 64, 68, 72  out: bit 0 */
+  uint8_t status;           /*  76  out: SHIPENV_ST_* of the step */
+  uint8_t pad3;
+  int16_t taken;            /*  78  (used by the facade's sample_action path) */
+  uint8_t words;            /*  80  (the same) */
+  uint8_t pad4[3];
+  int16_t next_action;      /*  84  out: what sample_action would return after this step (-2 when it fails) */
+  uint8_t next_words;       /*  86  out: words that draw consumed */
+  uint8_t next_status;      /*  87  out: its SHIPENV_ST_* */
+  uint8_t pad5[40];
+} shipenv_host_block;       /* 128 bytes */
+int shipenv_serve_step(shipenv_ctx *ctx, shipenv_host_block *block, uint64_t seed, uint64_t env_id, int max_steps,
+                       uint32_t flags, uint32_t word0);
+/* Makes the server kernel exit now (it is launched again by the next shipenv_serve_step) and waits for it. */
+int shipenv_serve_stop(shipenv_ctx *ctx);
+/* Idle time after which the server kernel retires, in microseconds (applies from its next launch). */
+int shipenv_serve_set_idle_us(shipenv_ctx *ctx, uint32_t idle_us);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,9 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_uint32,
                                       C.c_uint32, C.c_void_p]),
     "shipenv_step_host_workspace": (C.c_size_t, [C.c_int64]),
+    "shipenv_serve_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32]),
+    "shipenv_serve_stop": (C.c_int, [C.c_void_p]),
+    "shipenv_serve_set_idle_us": (C.c_int, [C.c_void_p, C.c_uint32]),
     "shipenv_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int64, C.c_int,
                                     C.c_uint32, C.c_int, C.c_void_p]),
@@ -154,6 +157,7 @@ class Context:
         h = C.c_void_p()
         check(lib().shipenv_ctx_create(self.device, C.byref(h)))
         self._h = h
+        self._serve = lib().shipenv_serve_step
         self.P = -1
         self.shape = None
 
@@ -232,6 +236,18 @@ class Context:
 
     def synchronize(self, stream):
         check(lib().shipenv_stream_synchronize(self._h, stream))
+
+    def serve_step(self, block_host_ptr, seed, env_id, max_steps, flags, word0):
+        """``shipenv_serve_step``: the N = 1 step + look-ahead sample answered by the resident server kernel."""
+        rc = self._serve(self._h, block_host_ptr, seed, env_id, max_steps, flags, word0)
+        if rc:
+            check(rc)
+
+    def serve_stop(self):
+        check(lib().shipenv_serve_stop(self._h))
+
+    def serve_set_idle_us(self, idle_us):
+        check(lib().shipenv_serve_set_idle_us(self._h, int(idle_us)))
 
     def sample_action(self, ships, clock, actions, words_used, status, seed, env_id_base, n, word0, stream):
         check(lib().shipenv_sample_action(self._h, ships, clock, actions, words_used, status, seed, env_id_base,

@@ -142,6 +142,103 @@ __global__ void __launch_bounds__(kThreads) step_sample_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------
+// The same, served: a resident one-warp kernel that answers step requests from a page-locked mailbox
+// (shipenv_serve_step).  A launch and a stream synchronisation cost the N = 1 facade ~20 us per step, the
+// transition itself a few; here the host writes a 64-byte request line, the warp sees it with its next poll (one
+// 64-byte read over PCIe), lane 0 runs the general path and the look-ahead sample_action, the warp writes a
+// 64-byte answer line and then -- behind a system-scope fence -- the sequence number the host spins on.
+// The request carries the whole env (ship, clock, seed, env id), so the server has no state but the world in its
+// shared memory.  It retires after idle_ns without a request (alive := 0) and is relaunched by the host.
+//   request  words 0..15 : ship[4], clock, action, word0, flags, max_steps, seed lo/hi, env id lo/hi, -, cmd, seq
+//   answer   words 16..31: ship[4], clock, status | next_status << 8 | next_words << 16 | done << 24 | reset << 25 |
+//                          error << 26, reward lo/hi, next_action, -, -, -, -, -, alive, ack
+// ------------------------------------------------------------------------------------------
+struct ServerArgs {
+  uint32_t* mailbox;        // device address of the page-locked 128-byte mailbox
+  const void* world; uint32_t world_bytes;
+  uint32_t last_seq;        // the last request that has been answered already
+  unsigned long long idle_ns;
+};
+enum : uint32_t { kSrvCmdStep = 1u, kSrvCmdQuit = 2u, kSrvSeq = 15u, kSrvCmd = 14u, kSrvAlive = 30u, kSrvAck = 31u };
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(32) step_server_kernel(const __grid_constant__ ServerArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t world_bar;
+  __shared__ uint32_t rk_s[20];
+  __shared__ uint32_t out_s[16];
+  stage_world(smem, a.world, a.world_bytes, &world_bar);
+  const WorldView w(smem);
+  const int lane = threadIdx.x;
+  uint32_t last = a.last_seq;
+  bool quit = false;
+  unsigned long long t_idle = global_timer_ns();
+  for (;;) {
+    const uint32_t v = lane < 16 ? ld_volatile_u32(a.mailbox + lane) : 0u;      // the request line, one read
+    const uint32_t seq = __shfl_sync(0xFFFFFFFFu, v, kSrvSeq);
+    if (seq == last) {
+      if (global_timer_ns() - t_idle > a.idle_ns) break;
+      continue;
+    }
+    last = seq;
+    if (__shfl_sync(0xFFFFFFFFu, v, kSrvCmd) == kSrvCmdQuit) { quit = true; break; }
+    uint4 rec;
+    rec.x = __shfl_sync(0xFFFFFFFFu, v, 0); rec.y = __shfl_sync(0xFFFFFFFFu, v, 1);
+    rec.z = __shfl_sync(0xFFFFFFFFu, v, 2); rec.w = __shfl_sync(0xFFFFFFFFu, v, 3);
+    uint32_t c = __shfl_sync(0xFFFFFFFFu, v, 4);
+    const int act = int(int16_t(__shfl_sync(0xFFFFFFFFu, v, 5) & 0xFFFFu));
+    const uint32_t word0 = __shfl_sync(0xFFFFFFFFu, v, 6), flags = __shfl_sync(0xFFFFFFFFu, v, 7);
+    const int max_steps = int(__shfl_sync(0xFFFFFFFFu, v, 8));
+    const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, v, 9), k1 = __shfl_sync(0xFFFFFFFFu, v, 10);
+    const uint64_t id = uint64_t(__shfl_sync(0xFFFFFFFFu, v, 11)) | (uint64_t(__shfl_sync(0xFFFFFFFFu, v, 12)) << 32);
+    if (lane < 10) { rk_s[2 * lane] = k0 + uint32_t(lane) * kPhiloxW0; rk_s[2 * lane + 1] = k1 + uint32_t(lane) * kPhiloxW1; }
+    __syncwarp();
+    if (lane == 0) {
+      ShipR s = unpack(rec);
+      const GeneralOut o = step_general_core(w, rk_s, id, word0, max_steps, flags, s, c, act);
+      const uint32_t w0n = (o.flags & kFlagError) ? word0 : 0u;      // a rejected step consumed nothing
+      Rng g;
+      g.seek(rk_s, c, id, w0n);
+      int cat = kCatJunk, val = 0;
+      const int st = w.h->P == 0 ? SHIPENV_ST_NO_PORTS : sample_action(w, s, g, cat, val);
+      const int next = st == SHIPENV_ST_OK ? encode_action(cat, val, w.h->P) : -2;
+      const uint4 fin = pack(s);
+      out_s[0] = fin.x; out_s[1] = fin.y; out_s[2] = fin.z; out_s[3] = fin.w;
+      out_s[4] = c;
+      out_s[5] = uint32_t(o.status & 255) | (uint32_t(st & 255) << 8) | (((g.i - w0n) & 255u) << 16) |
+                 ((o.flags & kFlagDone) ? 1u << 24 : 0u) | ((o.flags & kFlagReset) ? 1u << 25 : 0u) |
+                 ((o.flags & kFlagError) ? 1u << 26 : 0u);
+      out_s[6] = uint32_t(__double2loint(o.reward)); out_s[7] = uint32_t(__double2hiint(o.reward));
+      out_s[8] = uint32_t(uint16_t(int16_t(next)));
+    }
+    __syncwarp();
+    if (lane >= 16 && lane < 16 + 9) st_volatile_u32(a.mailbox + lane, out_s[lane - 16]);
+    __threadfence_system();                          // the answer before its sequence number
+    if (lane == 0) st_volatile_u32(a.mailbox + kSrvAck, seq);
+    t_idle = global_timer_ns();
+  }
+  // retiring: the host sees alive == 0 (and, for a quit request, its acknowledgement) and launches a new server
+  if (lane == 0) {
+    st_volatile_u32(a.mailbox + kSrvAlive, 0u);
+    __threadfence_system();
+    if (quit) st_volatile_u32(a.mailbox + kSrvAck, last);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // DQN valid-action mask (agents/dqn.py:125-175), one env per thread, ceil(A/32) words per env
 // ------------------------------------------------------------------------------------------
 struct ValidArgs {

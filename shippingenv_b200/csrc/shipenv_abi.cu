@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
@@ -18,6 +19,11 @@
 #include "kernels.cuh"
 
 using namespace shipenv;
+
+static_assert(sizeof(shipenv_host_block) == 128 && offsetof(shipenv_host_block, clock) == 32 &&
+              offsetof(shipenv_host_block, action) == 48 && offsetof(shipenv_host_block, done_bits) == 64 &&
+              offsetof(shipenv_host_block, status) == 76 && offsetof(shipenv_host_block, next_action) == 84,
+              "shipenv_host_block is the facade's page-locked block (shippingenv_b200/environment.py)");
 
 namespace {
 
@@ -96,6 +102,16 @@ struct shipenv_ctx {
   std::vector<unsigned char> h_world;
   uint32_t world_bytes = 0;
   bool dirty = true;
+  uint64_t world_gen = 1;        // bumped by every shipenv_set_*: the step server restarts when it has changed
+  // shipenv_serve_step: the mailbox (page-locked, device-mapped), the server kernel's stream and what the host knows
+  // about the kernel
+  volatile uint32_t* srv_mail = nullptr;
+  uint32_t* srv_mail_dev = nullptr;
+  cudaStream_t srv_stream = nullptr;
+  uint32_t srv_seq = 0;
+  bool srv_launched = false;
+  uint64_t srv_world_gen = 0;
+  uint32_t srv_idle_us = 2000;
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
@@ -303,8 +319,11 @@ int shipenv_ctx_create(int device, shipenv_ctx** out) {
 
 int shipenv_ctx_destroy(shipenv_ctx* c) {
   if (!c) return 0;
+  shipenv_serve_stop(c);
   {
     DeviceGuard guard(c->device);
+    if (c->srv_stream) cudaStreamDestroy(c->srv_stream);
+    if (c->srv_mail) cudaFreeHost(const_cast<uint32_t*>(c->srv_mail));
     if (c->d_world) cudaFree(c->d_world);
     if (c->d_tile_counter) cudaFree(c->d_tile_counter);
     if (c->world_event) cudaEventDestroy(c->world_event);
@@ -324,6 +343,7 @@ int shipenv_set_map(shipenv_ctx* c, const uint8_t* passable, int W, int H) {
   c->W = W; c->H = H;
   c->passable.assign(passable, passable + size_t(W) * H);
   c->dirty = true;
+  ++c->world_gen;
   return 0;
 }
 
@@ -335,6 +355,7 @@ int shipenv_set_ports(shipenv_ctx* c, const uint8_t* px, const uint8_t* py, cons
   for (int p = 0; p < P; ++p) { c->px[p] = px[p]; c->py[p] = py[p]; c->pfuel[p] = pfuel[p]; c->pcargo[p] = pcargo[p]; }
   c->P = P;
   c->dirty = true;
+  ++c->world_gen;
   return 0;
 }
 
@@ -344,6 +365,7 @@ int shipenv_set_consts(shipenv_ctx* c, const shipenv_consts* k) {
   if (v.capacity < 1 || v.capacity > SHIPENV_MAX_CAPACITY) return fail(SHIPENV_E_ARG, "capacity %d outside 1..%d", v.capacity, SHIPENV_MAX_CAPACITY);
   c->consts = v;
   c->dirty = true;
+  ++c->world_gen;
   return 0;
 }
 
@@ -686,6 +708,107 @@ int shipenv_step_sample(shipenv_ctx* c, shipenv_ship* ships, uint32_t* clock, co
   step_sample_kernel<<<grid, kThreads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   ++g_launches;
+  return 0;
+}
+
+// ---- the step server (aux_kernels.cuh: step_server_kernel) ----
+static int serve_launch(shipenv_ctx* c) {
+  ServerArgs a{c->srv_mail_dev, c->d_world, c->world_bytes, c->srv_seq - 1u, (unsigned long long)c->srv_idle_us * 1000ull};
+  c->srv_mail[kSrvAlive] = 1u;
+  step_server_kernel<<<1, 32, c->world_bytes, c->srv_stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  c->srv_launched = true;
+  ++g_launches;
+  return 0;
+}
+
+int shipenv_serve_stop(shipenv_ctx* c) {
+  if (int rc = check_ctx(c)) return rc;
+  if (!c->srv_mail || !c->srv_launched) return 0;
+  DeviceGuard guard(c->device);
+  if (c->srv_mail[kSrvAlive] != 0u) {               // still polling: ask it to leave
+    c->srv_mail[kSrvCmd] = kSrvCmdQuit;
+    std::atomic_thread_fence(std::memory_order_release);
+    c->srv_mail[kSrvSeq] = ++c->srv_seq;
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->srv_stream));   // retired (by the request or by its idle limit) and gone
+  c->srv_launched = false;
+  return 0;
+}
+
+int shipenv_serve_set_idle_us(shipenv_ctx* c, uint32_t idle_us) {
+  if (int rc = check_ctx(c)) return rc;
+  c->srv_idle_us = idle_us < 10u ? 10u : idle_us;
+  return 0;
+}
+
+int shipenv_serve_step(shipenv_ctx* c, shipenv_host_block* block, uint64_t seed, uint64_t env_id, int max_steps,
+                       uint32_t flags, uint32_t word0) {
+  if (int rc = check_ctx(c)) return rc;
+  if (!block) return fail(SHIPENV_E_ARG, "serve_step: null block");
+  if (max_steps < 0 || max_steps > 65535) return fail(SHIPENV_E_ARG, "max_steps %d outside 0..65535", max_steps);
+  if ((flags & SHIPENV_F_AUTO_RESET) && c->P < 2) return fail(SHIPENV_E_STATE, "auto-reset needs at least 2 ports");
+  DeviceGuard guard(c->device);
+  if (!c->srv_mail) {
+    void* h = nullptr;
+    CUDA_TRY(cudaHostAlloc(&h, 128, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(h, 0, 128);
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaFreeHost(h); return fail(SHIPENV_E_CUDA, "serve_step: mailbox is not device-visible"); }
+    if (cudaStreamCreateWithFlags(&c->srv_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFreeHost(h); return fail(SHIPENV_E_CUDA, "serve_step: no stream"); }
+    c->srv_mail = static_cast<volatile uint32_t*>(h);
+    c->srv_mail_dev = static_cast<uint32_t*>(d);
+  }
+  if (c->srv_world_gen != c->world_gen || c->dirty) {
+    // the world has changed: the resident kernel holds the old one in its shared memory
+    if (int rc = shipenv_serve_stop(c)) return rc;
+    if (int rc = sync_world(c, c->srv_stream)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->srv_stream));
+    c->world_pending = false;                        // (the upload, wherever it was issued, has been waited for)
+    c->srv_world_gen = c->world_gen;
+  }
+  volatile uint32_t* m = c->srv_mail;
+  const uint32_t* ship = reinterpret_cast<const uint32_t*>(&block->ship);
+  m[0] = ship[0]; m[1] = ship[1]; m[2] = ship[2]; m[3] = ship[3];
+  m[4] = block->clock;
+  m[5] = uint32_t(uint16_t(block->action));
+  m[6] = word0; m[7] = flags; m[8] = uint32_t(max_steps);
+  m[9] = uint32_t(seed); m[10] = uint32_t(seed >> 32);
+  m[11] = uint32_t(env_id); m[12] = uint32_t(env_id >> 32);
+  m[kSrvCmd] = kSrvCmdStep;
+  std::atomic_thread_fence(std::memory_order_release);   // the request before its sequence number
+  const uint32_t seq = ++c->srv_seq;
+  m[kSrvSeq] = seq;
+  if (!c->srv_launched || m[kSrvAlive] == 0u) {
+    if (c->srv_launched) CUDA_TRY(cudaStreamSynchronize(c->srv_stream));   // the retired kernel has left
+    if (int rc = serve_launch(c)) return rc;
+  }
+  // spin for the answer; a kernel that retires under our eyes is replaced (the request is still in the mailbox)
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t spins = 0; m[kSrvAck] != seq; ++spins) {
+    if ((spins & 1023u) == 1023u) {
+      if (m[kSrvAlive] == 0u && m[kSrvAck] != seq) {
+        CUDA_TRY(cudaStreamSynchronize(c->srv_stream));
+        if (m[kSrvAck] == seq) break;
+        if (int rc = serve_launch(c)) return rc;
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) {
+        const cudaError_t e = cudaStreamQuery(c->srv_stream);
+        return fail(SHIPENV_E_CUDA, "serve_step: no answer from the server kernel within 10 s (%s)",
+                    e == cudaSuccess || e == cudaErrorNotReady ? "kernel alive or retired" : cudaGetErrorString(e));
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  uint32_t* out = reinterpret_cast<uint32_t*>(&block->ship);
+  out[0] = m[16]; out[1] = m[17]; out[2] = m[18]; out[3] = m[19];
+  block->clock = m[20];
+  const uint32_t st = m[21];
+  block->status = uint8_t(st); block->next_status = uint8_t(st >> 8); block->next_words = uint8_t(st >> 16);
+  block->done_bits = (st >> 24) & 1u; block->reset_bits = (st >> 25) & 1u; block->error_bits = (st >> 26) & 1u;
+  const uint64_t rbits = uint64_t(m[22]) | (uint64_t(m[23]) << 32);
+  memcpy(&block->reward, &rbits, 8);
+  block->next_action = int16_t(uint16_t(m[24]));
   return 0;
 }
 

@@ -15,6 +15,7 @@ moves must be one of the four unit moves; ``reset`` with fewer than two ports ra
 looping forever; ``sample_action`` with ``fuel == 0`` at a port raises ``TypeError`` like the
 reference does, but never consumes a draw.
 """
+import os
 import random as _pyrandom
 import struct
 
@@ -44,6 +45,9 @@ _SHIP_FMT = struct.Struct("<BBBBid")            # shipenv_ship: x, y, origin, de
 _U32, _I16, _F64 = struct.Struct("<I"), struct.Struct("<h"), struct.Struct("<d")
 _NEXT_FMT = struct.Struct("<hBB")                # step_sample: next action, words it used, its status
 _FLAGS_FMT = struct.Struct("<IIIBxhB")           # done, reset, error words, status, taken, words used
+
+# SHIPENV_NO_SERVER=1: every step() is one shipenv_step_sample launch + one stream synchronisation (A/B, debugging)
+_USE_SERVER = os.environ.get("SHIPENV_NO_SERVER") != "1"
 
 _contexts = {}   # device index -> (Context, world signature currently uploaded)
 
@@ -84,12 +88,14 @@ class Environment:
         self._host = torch.zeros(_BLOCK, dtype=torch.uint8).pin_memory()
         self._hnp = self._host.numpy()
         self._buf = memoryview(self._hnp)
-        self._base = nat.host_device_pointer(self._host.data_ptr())
+        self._host_ptr = self._host.data_ptr()
+        self._base = nat.host_device_pointer(self._host_ptr)
         self._io = nat.StepIO()
         self._io.reward_f64, self._io.status = self._ptr(_REWARD), self._ptr(_STATUS)
         self._io.done_bits, self._io.reset_bits, self._io.error_bits = self._ptr(_DONE), self._ptr(_RESET), self._ptr(_ERR)
         self._passable_key = None
         self._passable = None
+        self._w_game = self._w_ports = self._w_fuel = self._w_cargo = None   # what _sync_world last saw
 
     # ------------------------------------------------------------------ construction
     def _is_within_map(self, x, y):
@@ -113,6 +119,13 @@ class Environment:
 
     # ------------------------------------------------------------------ host <-> device
     def _sync_world(self):
+        slot = _context(self._device.index)
+        # fast path (every step of an agent's loop): the same grid object, the same port tables, and the context still
+        # holds this world
+        if (self.np_game is self._w_game and slot[1] is self._world_sig and self._world_sig is not None
+                and self.port_positions == self._w_ports and self.port_fuel == self._w_fuel
+                and self.port_cargo == self._w_cargo):
+            return slot[0]
         # keyed on the array object itself (held, so its id cannot be recycled) and the port count: the passable set
         # only changes when np_game is replaced or add_port stamps a cell (it never shrinks)
         key = (self.np_game, len(self.port_positions))
@@ -127,7 +140,6 @@ class Environment:
         ports = [(int(p[0]), int(p[1])) for p in self.port_positions]
         sig = (self._passable_bytes, tuple(ports), tuple(map(int, self.port_fuel)),
                tuple(map(int, self.port_cargo)))
-        slot = _context(self._device.index)
         if slot[1] != sig:
             if len(ports) > nat.MAX_PORTS:
                 raise ValueError(f"at most {nat.MAX_PORTS} ports")
@@ -135,6 +147,9 @@ class Environment:
             slot[0].set_ports(ports, list(map(int, self.port_fuel)), list(map(int, self.port_cargo)))
             slot[1] = sig
         self._world_sig = slot[1]
+        self._w_game = self.np_game
+        self._w_ports = [list(p) for p in self.port_positions]
+        self._w_fuel, self._w_cargo = list(self.port_fuel), list(self.port_cargo)
         return slot[0]
 
     def _pack(self, action=0):
@@ -205,14 +220,20 @@ class Environment:
         self.ship_position = current_port                            # aliases the port's list, like :241
         return self._build_state()
 
+    def _snapshot(self):
+        """What the look-ahead draw of step() was made for: the attributes an agent could have changed since."""
+        pos = self.ship_position
+        return (pos[0], pos[1], self.origin_port_index, self.destination_port_index, self.cargo, self.fuel,
+                self._clock, self._word, self._world_sig) if len(pos) == 2 else None
+
     def sample_action(self):
         ctx = self._sync_world()
-        self._pack()
         spec, self._spec = self._spec, None
-        if spec is not None and spec[0] == self._buf[_SHIP:_SHIP + 16] and spec[1:] == (self._clock, self._word, self._world_sig):
+        if spec is not None and spec == self._snapshot():
             # the previous step() already drew this call's action for exactly this state (shipenv_step_sample)
             taken, words, status = _NEXT_FMT.unpack_from(self._buf, _NEXT)
         else:
+            self._pack()
             ctx.sample_action(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_TAKEN), self._ptr(_WORDS),
                               self._ptr(_STATUS), self._seed, self._env_id, 1, self._word, self._stream())
             self._wait(ctx)
@@ -271,20 +292,23 @@ class Environment:
         old = (int(self.ship_position[0]), int(self.ship_position[1])) if len(self.ship_position) == 2 else None
         fuel_was_int = isinstance(self.fuel, int)
         self._pack(a)
-        # the step and, in the same launch, the draw of the sample_action() call that usually follows it
-        ctx.step_sample(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_ACTION), self._io, self._ptr(_NEXT),
-                        self._ptr(_NEXT + 2), self._ptr(_NEXT + 3), self._seed, self._env_id, 1, 0, 0, self._word,
-                        self._stream())
-        self._wait(ctx)
+        # the step and, with it, the draw of the sample_action() call that usually follows it
+        if _USE_SERVER:
+            # answered by the resident server kernel of this device (no launch, no stream synchronisation)
+            ctx.serve_step(self._host_ptr, self._seed, self._env_id, 0, 0, self._word)
+        else:
+            ctx.step_sample(self._ptr(_SHIP), self._ptr(_CLOCK), self._ptr(_ACTION), self._io, self._ptr(_NEXT),
+                            self._ptr(_NEXT + 2), self._ptr(_NEXT + 3), self._seed, self._env_id, 1, 0, 0, self._word,
+                            self._stream())
+            self._wait(ctx)
         x, y, origin, dest, cargo, fuel = self._unpack()
         done_word, _, _, status, _, _ = _FLAGS_FMT.unpack_from(self._buf, _DONE)
         if status != nat.ST_OK:       # nothing changed on the device, no draw was consumed: the cell continues
-            self._spec = (bytes(self._buf[_SHIP:_SHIP + 16]), self._clock, self._word, self._world_sig)
+            self._spec = self._snapshot()
             exc, msg = _ERRORS[status]
             raise exc(msg)
         self._clock = _U32.unpack_from(self._buf, _CLOCK)[0]
         self._word = 0
-        self._spec = (bytes(self._buf[_SHIP:_SHIP + 16]), self._clock, 0, self._world_sig)
         moved = (x, y) != old
         keep_int = fuel_was_int and not (action[0] == ActionType.MOVE_SHIP and moved)
         self._adopt(x, y, origin, dest, cargo, fuel, keep_int_fuel=keep_int)
@@ -292,6 +316,7 @@ class Environment:
             self.ship_position = [x, y]                                               # a fresh list, like :297
             self.np_game[old[0], old[1]] = Entity.TRAVEL                              # :303-304
             self.np_game[x, y] = Entity.BOAT
+        self._spec = self._snapshot()
         reward = _F64.unpack_from(self._buf, _REWARD)[0]
         return self._build_state(), reward, bool(done_word & 1), {}
 

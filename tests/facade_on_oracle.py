@@ -65,6 +65,22 @@ class OracleContext:
         _view(next_words, np.uint8, n)[:] = wu
         _view(next_status, np.uint8, n)[:] = st
 
+    def serve_step(self, block, seed, env_id, max_steps, flags, word0):
+        """shipenv_serve_step on the 128-byte host block (include/shipenv.h: shipenv_host_block)."""
+        self.launches += 1
+        o = self._oracle()
+        s, c = _view(block, orc.SHIP_DTYPE), _view(block + 32, np.uint32)
+        r = o.step(s, c, _view(block + 48, np.int16).copy(), seed, env_id, max_steps, bool(flags & 1), word0)
+        _view(block + 16, np.float64)[:] = r["reward"]
+        _view(block + 76, np.uint8)[:] = r["status"]
+        _view(block + 64, np.uint32)[0] = int(r["done"][0])
+        _view(block + 68, np.uint32)[0] = int(r["reset"][0])
+        _view(block + 72, np.uint32)[0] = int(r["status"][0] != 0)
+        a, wu, st = o.sample_action(s, c, seed, env_id, word0 if r["status"][0] != 0 else 0)
+        _view(block + 84, np.int16)[:] = a
+        _view(block + 86, np.uint8)[:] = wu
+        _view(block + 87, np.uint8)[:] = st
+
     def synchronize(self, stream):
         pass
 

@@ -256,6 +256,58 @@ def test_facade_mcts_extensions_match_batched_kernels():
         assert before == (list(env.ship_position), env.fuel, env.cargo, env._clock)   # planning never moves the env
 
 
+def test_step_server_lifecycle_and_equivalence():
+    """step() is answered by the resident server kernel (shipenv_serve_step).  Two envs that share it, interleaved,
+    against two envs stepped by one shipenv_step_sample launch per call: same states, rewards, dones, exceptions and
+    look-ahead draws -- across server retirement (idle limit), an explicit stop, a device-wide synchronisation and a
+    change of the world (the server restarts with the new one)."""
+    import time
+    import torch
+    import shippingenv_b200.environment as E
+    from shippingenv_b200 import ActionType
+
+    def drive(use_server, log):
+        E._USE_SERVER = use_server
+        a, b = make_env(11, env_id=3), make_env(12, env_id=4)
+        ctx = a._sync_world()
+        ctx.serve_set_idle_us(300)
+        a.reset(); b.reset()
+        for t in range(400):
+            for env in (a, b):
+                act = env.sample_action() if t % 7 else [ActionType.MOVE_SHIP, (0, 1)]
+                try:
+                    s, r, d, _ = env.step(act)
+                    log.append((t, bits(r), d, tuple(env.ship_position), env.cargo, bits(env.fuel), env._clock))
+                    if d:
+                        env.reset()
+                except Exception as exc:
+                    log.append((t, type(exc).__name__, str(exc)))
+            if t == 50:
+                time.sleep(0.01)                     # the server retires (idle limit 300 us) and comes back
+            if t == 100 and use_server:
+                ctx.serve_stop()
+            if t == 150:
+                torch.cuda.synchronize()             # returns: the server leaves after its idle limit
+            if t == 200:                             # another world on the same context: one more port
+                c = make_env(13, env_id=5, ports=PORTS + [[30, 30]], stock=False)
+                c.reset()
+                for _ in range(20):
+                    try:
+                        s, r, d, _ = c.step(c.sample_action())
+                        log.append(("c", bits(r), d, tuple(c.ship_position), c.cargo, bits(c.fuel), c._clock))
+                    except Exception as exc:
+                        log.append(("c", type(exc).__name__))
+        ctx.serve_set_idle_us(2000)
+
+    try:
+        served, launched = [], []
+        drive(True, served)
+        drive(False, launched)
+    finally:
+        E._USE_SERVER = os.environ.get("SHIPENV_NO_SERVER") != "1"
+    assert len(served) > 800 and served == launched
+
+
 REF = os.environ.get("SHIPPINGENV_REF", "/root/reference")
 
 
