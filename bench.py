@@ -586,8 +586,15 @@ def run_extras(torch, dev, g0, pool, block, gen, n):
     extras = {}
 
     def timed(fn, reps):
-        for _ in range(3):                 # warm-up: the caching allocator has the output buffers of two calls by then
+        # warm-up: at least three calls (the caching allocator then has the output buffers of two calls) and at least
+        # 100 ms of GPU work -- after host-side set-up the SM clock has dropped to idle and takes tens of
+        # milliseconds to come back (measured: 120 -> 330 -> 990 -> 1965 MHz)
+        t_warm, calls = time.perf_counter(), 0
+        while calls < 3 or time.perf_counter() - t_warm < 0.1:
             fn()
+            calls += 1
+            if calls % 8 == 0:
+                torch.cuda.synchronize(dev)
         torch.cuda.synchronize(dev)
         e0.record()
         for _ in range(reps):

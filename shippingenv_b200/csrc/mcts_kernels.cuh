@@ -26,7 +26,9 @@ __device__ __forceinline__ int rollout_attempt(const WorldView& w, ShipR& s, G& 
   const int W = w.h->W, H = w.h->H, cap = w.h->capacity;
   if (s.dest == kNone || s.cargo < 0 || unsigned(s.x) >= unsigned(W) || unsigned(s.y) >= unsigned(H)) return 2;
   const bool on_port = w.port_cell(s.x, s.y);
-  const uint32_t w0 = g.peek(0);
+  const uint32_t* const win = g.window();              // the next words of the stream: win[k * stride]
+  constexpr uint32_t kS = G::kColumnStride;
+  const uint32_t w0 = win[0];
   if (on_port) {                                       // sample_action looks at the port first (:247-260)
     if (s.cargo != 0) {
       if (s.fuel == 0.0) return 2;                     // :258-260 -> :163
@@ -44,7 +46,7 @@ __device__ __forceinline__ int rollout_attempt(const WorldView& w, ShipR& s, G& 
   const int dx = (m & 1) * (m - 2), dy = ((m & 1) ^ 1) * (m - 1);
   const int nx = s.x + dx, ny = s.y + dy;
   if (unsigned(nx) >= unsigned(W) || unsigned(ny) >= unsigned(H)) { g.advance(1); return 1; }   // :284
-  const uint32_t w1 = g.peek(1), w2 = g.peek(2), w3 = g.peek(3), w4 = g.peek(4), w5 = g.peek(5), w6 = g.peek(6);
+  const uint32_t w1 = win[kS], w2 = win[2 * kS], w3 = win[3 * kS], w4 = win[4 * kS], w5 = win[5 * kS], w6 = win[6 * kS];
   const double cost = __dadd_rn(1.0, __dadd_rn(-0.1, __dmul_rn(0.1 - (-0.1), unit_double(w1))));   // :287, :103-104
   const bool no_fuel = s.fuel < cost;                                                   // :288
   const bool water = w.passable(nx, ny);                                                // :293
@@ -90,6 +92,7 @@ __device__ __forceinline__ int rollout_run(const WorldView& w, ShipR& s, G& g, i
   bool done = false;
   int fails = 0;
   while (!done && steps < L) {                     // agents/mcts.py:228
+    g.top_up();
     g.ensure(7);
     double reward = 0.0;
     int rc = w.h->P == 0 ? 2 : rollout_attempt(w, s, g, reward, done);
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
-  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [16][blockDim.x] words
+  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [32][blockDim.x] words
   const int64_t total = a.R * int64_t(a.S);
   const int64_t n_tiles = (total + kRolloutThreads - 1) / kRolloutThreads;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -143,8 +146,8 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
     const int64_t r = j / a.S;
     const int sim = int(j - r * a.S);
     ShipR s = unpack(__ldg(a.roots + r));
-    RngFifo g;
-    g.seek(a.round_key, fifo + threadIdx.x, blockDim.x, uint32_t(sim), a.root_id_base + uint64_t(r));
+    RngFifo<kRolloutThreads> g;
+    g.seek(a.round_key, fifo + threadIdx.x, uint32_t(sim), a.root_id_base + uint64_t(r));
     double total_reward;
     int steps;
     const int st = rollout_run(w, s, g, a.L, total_reward, steps);
@@ -216,8 +219,8 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
   __shared__ __align__(8) uint64_t world_bar;
   stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
-  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [16][blockDim.x] words
-  double* log_table = reinterpret_cast<double*>(fifo + RngFifo::kWords * kMctsThreads);
+  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [32][blockDim.x] words
+  double* log_table = reinterpret_cast<double*>(fifo + RngFifo<kMctsThreads>::kWords * kMctsThreads);
   for (int k = threadIdx.x; k < a.S + 2; k += kMctsThreads) log_table[k] = a.log_table[k];
   __syncthreads();
   for (int64_t r = blockIdx.x * int64_t(kMctsThreads) + threadIdx.x; r < a.R; r += int64_t(gridDim.x) * kMctsThreads) {
@@ -228,8 +231,8 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
     t.info[0] = uint8_t(mcts_moves_ok(root) ? 32 : 0);
     for (int sim = 0; sim < a.S && st == SHIPENV_ST_OK; ++sim) {
       ShipR s = root;                                                        // _create_env_copy, :257
-      RngFifo g;
-      g.seek(a.round_key, fifo + threadIdx.x, blockDim.x, uint32_t(sim), a.root_id_base + uint64_t(r));
+      RngFifo<kMctsThreads> g;
+      g.seek(a.round_key, fifo + threadIdx.x, uint32_t(sim), a.root_id_base + uint64_t(r));
       int node = 0;
       bool done = false;
       double rew = 0.0;

@@ -91,41 +91,51 @@ struct Rng {
 };
 
 // The same word stream behind a small FIFO in shared memory (16 words per thread, word-interleaved so that the
-// threads of a warp never conflict).  Long sequential consumers (rollouts, MCTS) call ensure() once per
+// threads of a warp never conflict).  Long sequential consumers (rollouts, MCTS) call top_up() + ensure() once per
 // environment step: every lane of the warp then refills at ONE code site, in lock-step, instead of each lane
 // running Philox at whichever of the many next() call sites it happens to cross a block boundary.  With
 // ensure(k) done, peek(0..k-1) reads ahead without consuming, so a step can be written as straight-line code that
 // looks at every word it might need and then advance()s by what it used.
+// The ring is mapped twice (every word is stored at p and p + 16 of a 32-word column): the words i .. i + 7 are
+// then contiguous for any i, and with the column stride a template constant a peek is one ld.shared with an
+// immediate offset from window() instead of an add, a mask and a multiply each.
+template <uint32_t kStride>
 struct RngFifo {
-  static constexpr uint32_t kWords = 16;   // ring size per thread
+  static constexpr uint32_t kRing = 16;            // words resident per thread
+  static constexpr uint32_t kWords = 2 * kRing;    // shared-memory words per thread (the ring is stored twice)
+  static constexpr uint32_t kColumnStride = kStride;
   const uint32_t* rk;
-  uint32_t* slot;          // this thread's column of the shared [kWords][blockDim.x] word array
-  uint32_t stride;         // blockDim.x
+  uint32_t* slot;          // this thread's column of the shared [kWords][kStride] word array
   uint32_t c1, c2, c3;
   uint32_t i;              // next word of the cell to hand out
   uint32_t filled;         // words generated so far (multiple of 4); words [filled-16, filled) are resident
 
-  __device__ __forceinline__ void seek(const uint32_t* round_keys, uint32_t* column, uint32_t column_stride,
-                                       uint32_t cell1, uint64_t id) {
-    rk = round_keys; slot = column; stride = column_stride;
+  __device__ __forceinline__ void seek(const uint32_t* round_keys, uint32_t* column, uint32_t cell1, uint64_t id) {
+    rk = round_keys; slot = column;
     c1 = cell1; c2 = uint32_t(id); c3 = uint32_t(id >> 32);
     i = 0; filled = 0;
   }
   __device__ __forceinline__ void refill() {
     uint32_t w[4];
     philox4x32_10(filled >> 2, c1, c2, c3, rk[0], rk[1], w);
-    const uint32_t base = filled & (kWords - 1u);      // 0, 4, 8 or 12
+    uint32_t* p = slot + (filled & (kRing - 1u)) * kStride;      // 0, 4, 8 or 12
 #pragma unroll
-    for (int k = 0; k < 4; ++k) slot[(base + k) * stride] = w[k];
+    for (int k = 0; k < 4; ++k) { p[k * kStride] = w[k]; p[(k + kRing) * kStride] = w[k]; }
     filled += 4;
   }
+  // One block for every lane that has room for it: the lanes of a warp consume 3 to 7 words per step, so refilling
+  // on demand runs the Philox code once or twice per step with part of the warp each time; here it runs once with
+  // (nearly) all lanes, and ensure() only picks up stragglers.
+  __device__ __forceinline__ void top_up() { if (filled - i <= kRing - 4u) refill(); }
   // at least `ahead` (<= 8) words resident beyond the read position
   __device__ __forceinline__ void ensure(uint32_t ahead = 4u) { while (filled - i < ahead) refill(); }
-  __device__ __forceinline__ uint32_t peek(uint32_t k) const { return slot[((i + k) & (kWords - 1u)) * stride]; }
+  // the words i, i + 1, ... as window()[k * kStride], k < 8 (valid after ensure(k + 1))
+  __device__ __forceinline__ const uint32_t* window() const { return slot + (i & (kRing - 1u)) * kStride; }
+  __device__ __forceinline__ uint32_t peek(uint32_t k) const { return window()[k * kStride]; }
   __device__ __forceinline__ void advance(uint32_t k) { i += k; }
   __device__ __forceinline__ uint32_t next() {
     if (i == filled) refill();                         // rare: a step that needs more than the words ahead
-    const uint32_t w = slot[(i & (kWords - 1u)) * stride];
+    const uint32_t w = slot[(i & (kRing - 1u)) * kStride];
     ++i;
     return w;
   }

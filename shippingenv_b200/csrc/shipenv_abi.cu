@@ -897,7 +897,7 @@ int shipenv_rollout(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S,
   RolloutArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(roots), R, S, L, returns,
                 reinterpret_cast<uint4*>(final), steps, status, seed, root_id_base, {}};
   fill_round_keys(a.round_key, seed, kRolloutTweak);
-  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + RngFifo::kWords * 4 * kRolloutThreads;   // world + word FIFO
+  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + RngFifo<kRolloutThreads>::kWords * 4 * kRolloutThreads;   // world + word FIFO
   const int64_t tiles = (R * int64_t(S) + kRolloutThreads - 1) / kRolloutThreads;
   int grid = 0;
   if (int rc = grid_for(c, rollout_kernel, c->occ_rollout, kRolloutThreads, smem, tiles, &grid)) return rc;
@@ -927,7 +927,7 @@ int shipenv_mcts(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S, in
   for (int n = 1; n < S + 2; ++n) a.log_table[n] = log_table ? log_table[n] : std::log(double(n));
   fill_round_keys(a.round_key, seed, kRolloutTweak);
   // world + word FIFO + log table
-  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + RngFifo::kWords * 4 * kMctsThreads +
+  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + RngFifo<kMctsThreads>::kWords * 4 * kMctsThreads +
                       sizeof(double) * (SHIPENV_MCTS_MAX_SIMS + 2);
   const bool small_tree = S + 2 <= 64;               // one node per simulation plus the root
   void (*kernel)(const MctsArgs) = small_tree ? mcts_kernel<64> : mcts_kernel<128>;
