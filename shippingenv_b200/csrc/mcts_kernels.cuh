@@ -172,6 +172,7 @@ struct MctsArgs {
   uint64_t seed, root_id_base;
   uint32_t round_key[20];
   double log_table[SHIPENV_MCTS_MAX_SIMS + 2];   // log_table[n] = log(n) as the caller computes it (numpy.log)
+  int explore_table;                             // the exploration-term table fits in shared memory (S <= 64)
 };
 
 // One root's tree (agents/mcts.py:13-40), indexed by node id; at most one node per simulation plus the root, so the
@@ -179,6 +180,7 @@ struct MctsArgs {
 template <int kNodes>
 struct MctsTree {
   double total[kNodes];
+  double mean[kNodes];          // total / visits as of the last backpropagation through the node (UCB1's first term)
   uint8_t visits[kNodes];       // <= S <= 126
   uint8_t parent[kNodes];
   uint8_t info[kNodes];         // action (2 bits) | nchild << 2 (3 bits) | moves_ok << 5
@@ -193,21 +195,27 @@ __device__ __forceinline__ bool mcts_moves_ok(const ShipR& s) {
   return s.dest != kNone && !(s.fuel == 0.0 && s.origin != kNone);
 }
 
-// best_child (:109-128): UCB1, unvisited children first, np.argmax takes the first maximum
+// best_child (:109-128): UCB1, unvisited children first, np.argmax takes the first maximum.
+// value = total / n + c * sqrt(2 ln N / n), every operation rounded on its own as numpy does.  The divide and the
+// square root are long software sequences in fp64 (a selection step over four children cost ~1,200 instructions):
+// the first term is cached per node when its statistics change (backpropagation), the second depends on the two
+// visit counts only and comes from a table built once per CTA with the same operations,
+// explore[N * (N + 1) / 2 + n] for 1 <= n <= N <= S + 1 (null: S too large for the table, computed in place).
 template <int kNodes>
-__device__ __forceinline__ int mcts_best_child(const MctsTree<kNodes>& t, int node, double c_param, const double* log_table) {
+__device__ __forceinline__ int mcts_best_child(const MctsTree<kNodes>& t, int node, double c_param, const double* log_table,
+                                               const double* explore) {
   int best = 0;
   double best_v = 0.0;
-  const double two_log = __dmul_rn(2.0, log_table[t.visits[node]]);
+  const int N = t.visits[node];
+  const double two_log = __dmul_rn(2.0, log_table[N]);
   const int nc = t.nchild(node);
   for (int k = 0; k < nc; ++k) {
     const int ch = t.child[node][k];
+    const int n = t.visits[ch];
     double v;
-    if (t.visits[ch] == 0) v = __longlong_as_double(0x7FF0000000000000LL);
-    else {
-      const double n = double(t.visits[ch]);
-      v = __dadd_rn(__ddiv_rn(t.total[ch], n), __dmul_rn(c_param, __dsqrt_rn(__ddiv_rn(two_log, n))));
-    }
+    if (n == 0) v = __longlong_as_double(0x7FF0000000000000LL);
+    else if (explore && n <= N) v = __dadd_rn(t.mean[ch], c_param == 0.0 ? 0.0 : explore[N * (N + 1) / 2 + n]);
+    else v = __dadd_rn(t.mean[ch], __dmul_rn(c_param, __dsqrt_rn(__ddiv_rn(two_log, double(n)))));
     if (k == 0 || v > best_v) { best = ch; best_v = v; }
   }
   return best;
@@ -222,12 +230,24 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
   uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [32][blockDim.x] words
   double* log_table = reinterpret_cast<double*>(fifo + RngFifo<kMctsThreads>::kWords * kMctsThreads);
   for (int k = threadIdx.x; k < a.S + 2; k += kMctsThreads) log_table[k] = a.log_table[k];
+  // the exploration term c * sqrt(2 ln N / n) for every pair of visit counts a launch can meet
+  double* explore = a.explore_table ? log_table + (SHIPENV_MCTS_MAX_SIMS + 2) : nullptr;
+  if (explore) {
+    const int top = a.S + 1;                         // visits never exceed S; the root's reach S
+    for (int e = threadIdx.x; e < (top + 1) * (top + 2) / 2; e += kMctsThreads) {
+      int N = 0;
+      while ((N + 1) * (N + 2) / 2 <= e) ++N;        // e = N (N + 1) / 2 + n, 0 <= n <= N
+      const int n = e - N * (N + 1) / 2;
+      explore[e] = n == 0 ? 0.0
+                          : __dmul_rn(a.c_param, __dsqrt_rn(__ddiv_rn(__dmul_rn(2.0, a.log_table[N]), double(n))));
+    }
+  }
   __syncthreads();
   for (int64_t r = blockIdx.x * int64_t(kMctsThreads) + threadIdx.x; r < a.R; r += int64_t(gridDim.x) * kMctsThreads) {
     const ShipR root = unpack(__ldg(a.roots + r));
     MctsTree<kNodes> t;
     int n_nodes = 1, st = SHIPENV_ST_OK;
-    t.total[0] = 0.0; t.visits[0] = 0; t.parent[0] = 255;
+    t.total[0] = 0.0; t.mean[0] = 0.0; t.visits[0] = 0; t.parent[0] = 255;
     t.info[0] = uint8_t(mcts_moves_ok(root) ? 32 : 0);
     for (int sim = 0; sim < a.S && st == SHIPENV_ST_OK; ++sim) {
       ShipR s = root;                                                        // _create_env_copy, :257
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
         if (!t.moves_ok(node)) { st = SHIPENV_ST_MCTS_UNSUPPORTED; break; }
         if (t.nchild(node) != 4) break;
         g.ensure();
-        node = mcts_best_child(t, node, a.c_param, log_table);
+        node = mcts_best_child(t, node, a.c_param, log_table, explore);
         const int e = do_action(w, s, g, kCatMove, t.action(node), rew, done);
         if (e != SHIPENV_ST_OK || done) break;
       }
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
         const int e = do_action(w, s, g, kCatMove, act, rew, done);
         if (e != SHIPENV_ST_OK) continue;                                    // :278-279: the simulation is skipped
         const int ch = n_nodes++;
-        t.total[ch] = rew; t.visits[ch] = 0; t.parent[ch] = uint8_t(node);   // :144-146
+        t.total[ch] = rew; t.mean[ch] = 0.0; t.visits[ch] = 0; t.parent[ch] = uint8_t(node);   // :144-146
         t.info[ch] = uint8_t(act | (mcts_moves_ok(s) ? 32 : 0));
         t.child[node][nc] = uint8_t(ch);
         t.info[node] = uint8_t(t.info[node] + 4);                            // one more child
@@ -271,7 +291,11 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
       int steps;
       st = rollout_run(w, s, g, a.L, total, steps);
       if (st != SHIPENV_ST_OK) break;
-      for (int n = node; n != 255; n = t.parent[n]) { t.visits[n] += 1; t.total[n] = __dadd_rn(t.total[n], total); }   // :149-159
+      for (int n = node; n != 255; n = t.parent[n]) {                        // :149-159
+        t.visits[n] += 1;
+        t.total[n] = __dadd_rn(t.total[n], total);
+        t.mean[n] = __ddiv_rn(t.total[n], double(t.visits[n]));
+      }
     }
     const int nc0 = t.nchild(0);
     for (int k = 0; k < 4; ++k) {
@@ -285,7 +309,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
     int act = -1;
     if (st == SHIPENV_ST_OK) {
       if (nc0 == 0) st = SHIPENV_ST_MCTS_NO_CHILDREN;                        // :291-292
-      else act = t.action(mcts_best_child(t, 0, 0.0, log_table));            // :288-290
+      else act = t.action(mcts_best_child(t, 0, 0.0, log_table, explore));   // :288-290
     }
     a.action[r] = int16_t(act);
     a.status[r] = uint8_t(st);

@@ -926,9 +926,11 @@ int shipenv_mcts(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S, in
   a.log_table[0] = 0.0;
   for (int n = 1; n < S + 2; ++n) a.log_table[n] = log_table ? log_table[n] : std::log(double(n));
   fill_round_keys(a.round_key, seed, kRolloutTweak);
-  // world + word FIFO + log table
+  // world + word FIFO + log table (+ the table of UCB1 exploration terms for every pair of visit counts, S <= 64)
+  a.explore_table = S <= 64 ? 1 : 0;
   const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + RngFifo<kMctsThreads>::kWords * 4 * kMctsThreads +
-                      sizeof(double) * (SHIPENV_MCTS_MAX_SIMS + 2);
+                      sizeof(double) * (SHIPENV_MCTS_MAX_SIMS + 2) +
+                      (a.explore_table ? sizeof(double) * size_t(S + 2) * size_t(S + 3) / 2 : 0);
   const bool small_tree = S + 2 <= 64;               // one node per simulation plus the root
   void (*kernel)(const MctsArgs) = small_tree ? mcts_kernel<64> : mcts_kernel<128>;
   int grid = 0;
