@@ -53,8 +53,15 @@ extern "C" {
  *                    agents/mcts.py:228-236)
  *   [0x4000,0x6000)  TAKE_CARGO amount a-0x4000  (amounts the flat space cannot express)
  *   [0x6000,0x8000)  TAKE_FUEL  amount a-0x6000
+ *   [-32762,-2]      MOVE by any (dx, dy) with |dx|, |dy| <= 90, a = -2 - ((dx+90)*181 + (dy+90)): the reference's
+ *                    _move_ship takes any pair (shipping/environment.py:278-287); the fuel cost is then
+ *                    sqrt(dx^2+dy^2) * (1 + uniform(-0.1, 0.1)) and only the target cell's terrain is looked at
  *   anything else    rejected, SHIPENV_ST_UNKNOWN */
 #define SHIPENV_ACT_POLICY (-1)
+#define SHIPENV_ACT_NONE (-32768) /* output only: shipenv_sample_action / next_action when the draw failed (status says why) */
+#define SHIPENV_ACT_MOVE_XY_BASE (-2)
+#define SHIPENV_MOVE_XY_MAX 90
+#define SHIPENV_ACT_MOVE_XY(dx, dy) (SHIPENV_ACT_MOVE_XY_BASE - (((dx) + 90) * 181 + ((dy) + 90)))
 #define SHIPENV_ACT_EXT_CARGO 0x4000
 #define SHIPENV_ACT_EXT_FUEL 0x6000
 #define SHIPENV_N_CARGO_ACTIONS 50
@@ -314,7 +321,7 @@ typedef struct shipenv_host_block {
   int16_t taken;            /*  78  (used by the facade's sample_action path) */
   uint8_t words;            /*  80  (the same) */
   uint8_t pad4[3];
-  int16_t next_action;      /*  84  out: what sample_action would return after this step (-2 when it fails) */
+  int16_t next_action;      /*  84  out: what sample_action would return after this step (SHIPENV_ACT_NONE when it fails) */
   uint8_t next_words;       /*  86  out: words that draw consumed */
   uint8_t next_status;      /*  87  out: its SHIPENV_ST_* */
   uint8_t pad5[40];

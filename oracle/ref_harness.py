@@ -39,6 +39,11 @@ _MSG_TO_STATUS = {
 
 EXT_CARGO, EXT_FUEL = 0x4000, 0x6000  # extended action encodings (amount = a - base)
 POLICY = -1
+MOVE_XY_BASE = -2                     # a = -2 - ((dx + 90) * 181 + (dy + 90)), |dx|, |dy| <= 90
+
+
+def move_xy(dx, dy):
+    return MOVE_XY_BASE - ((int(dx) + 90) * 181 + (int(dy) + 90))
 
 
 def ref_root():
@@ -115,6 +120,9 @@ class RefBatch:
             return [AT.TAKE_CARGO, int(a) - EXT_CARGO]
         if EXT_FUEL <= a < 0x8000:
             return [AT.TAKE_FUEL, int(a) - EXT_FUEL]
+        if MOVE_XY_BASE - 181 * 181 < a <= MOVE_XY_BASE:      # any (dx, dy): _move_ship takes it as it is (:278-287)
+            k = MOVE_XY_BASE - int(a)
+            return [AT.MOVE_SHIP, (k // 181 - 90, k % 181 - 90)]
         return [99, 0]
 
     def encode(self, env, act):

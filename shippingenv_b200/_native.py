@@ -14,6 +14,9 @@ MAX_PORTS = 32
 MAX_DIM = 256
 NONE_PORT = 255
 ACT_POLICY = -1
+ACT_MOVE_XY_BASE = -2        # a = -2 - ((dx + 90) * 181 + (dy + 90)): MOVE_SHIP by any (dx, dy), |dx|, |dy| <= 90
+MOVE_XY_MAX = 90
+ACT_NONE = -32768            # output only: a failed sample_action draw
 ACT_EXT_CARGO = 0x4000
 ACT_EXT_FUEL = 0x6000
 N_CARGO_ACTIONS = 50

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const __grid_constant_
     g.seek(a.round_key, a.clock[i], a.env_id_base + uint64_t(i), a.word0);
     int cat = kCatJunk, val = 0;
     int st = w.h->P == 0 ? SHIPENV_ST_NO_PORTS : sample_action(w, s, g, cat, val);
-    a.actions[i] = st == SHIPENV_ST_OK ? int16_t(encode_action(cat, val, w.h->P)) : int16_t(-2);
+    a.actions[i] = st == SHIPENV_ST_OK ? int16_t(encode_action(cat, val, w.h->P)) : int16_t(SHIPENV_ACT_NONE);
     if (a.words_used) a.words_used[i] = uint8_t(g.i - a.word0);
     if (a.status) a.status[i] = uint8_t(st);
   }
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) step_sample_kernel(const __grid_cons
     g.seek(a.s.round_key, a.s.clock[i], a.s.env_id_base + uint64_t(uint32_t(i)), word0);
     int cat = kCatJunk, val = 0;
     const int st = w.h->P == 0 ? SHIPENV_ST_NO_PORTS : sample_action(w, s, g, cat, val);
-    a.next_action[i] = st == SHIPENV_ST_OK ? int16_t(encode_action(cat, val, w.h->P)) : int16_t(-2);
+    a.next_action[i] = st == SHIPENV_ST_OK ? int16_t(encode_action(cat, val, w.h->P)) : int16_t(SHIPENV_ACT_NONE);
     if (a.next_words) a.next_words[i] = uint8_t(g.i - word0);
     if (a.next_status) a.next_status[i] = uint8_t(st);
   }
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(32) step_server_kernel(const __grid_constant__
       g.seek(rk_s, c, id, w0n);
       int cat = kCatJunk, val = 0;
       const int st = w.h->P == 0 ? SHIPENV_ST_NO_PORTS : sample_action(w, s, g, cat, val);
-      const int next = st == SHIPENV_ST_OK ? encode_action(cat, val, w.h->P) : -2;
+      const int next = st == SHIPENV_ST_OK ? encode_action(cat, val, w.h->P) : SHIPENV_ACT_NONE;
       const uint4 fin = pack(s);
       out_s[0] = fin.x; out_s[1] = fin.y; out_s[2] = fin.z; out_s[3] = fin.w;
       out_s[4] = c;

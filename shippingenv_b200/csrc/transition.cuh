@@ -11,6 +11,9 @@
 namespace shipenv {
 
 enum : int { kCatMove = 1, kCatSelect = 2, kCatFuel = 3, kCatCargo = 4, kCatJunk = 99 };  // shipping/type.py:1-5
+// not a category of the reference: MOVE_SHIP with a move other than the four of ShipMove (any (dx, dy), :278-287);
+// the value is the offset k of the SHIPENV_ACT_MOVE_XY encoding, dx = k / 181 - 90, dy = k % 181 - 90
+constexpr int kCatMoveXY = 5;
 
 struct ShipR {  // an unpacked shipenv_ship
   int x, y, origin, dest, cargo;
@@ -57,16 +60,17 @@ __device__ __forceinline__ void env_reset(const WorldView& w, ShipR& s, G& g) {
   s.x = p & 255u; s.y = (p >> 8) & 255u;
 }
 
-// _move_ship (:273-339); m = 0..3 = N, E, S, W = (0,-1), (-1,0), (0,1), (1,0) (shipping/type.py:13-16).
-template <class G>
-__device__ __forceinline__ int do_move(const WorldView& w, ShipR& s, G& g, int m, double& reward, bool& done) {
+// _move_ship (:273-339) by (dx, dy).  kUnit: one of the four moves of ShipMove, whose distance is exactly 1.
+template <bool kUnit, class G>
+__device__ __forceinline__ int do_move_xy(const WorldView& w, ShipR& s, G& g, int dx, int dy, double& reward, bool& done) {
   if (s.dest == kNone) return SHIPENV_ST_NO_DEST;                               // :276
-  const int dx = (m == 3) - (m == 1), dy = (m == 2) - (m == 0);
   const int sx = s.x, sy = s.y, nx = sx + dx, ny = sy + dy;
   if (unsigned(nx) >= unsigned(w.h->W) || unsigned(ny) >= unsigned(w.h->H)) return SHIPENV_ST_OFF_MAP;  // :284
-  // :287 -> :103-104: sqrt(1) * (1 + uniform(-0.1, 0.1)), uniform = a + (b - a) * random()
+  // :287 -> :103-104: sqrt(dx^2 + dy^2) * (1 + uniform(-0.1, 0.1)), uniform = a + (b - a) * random().  np.sqrt is
+  // correctly rounded, like __dsqrt_rn; for a unit move the distance is 1.0 and the product is its other factor.
   const double u = __dadd_rn(-0.1, __dmul_rn(0.1 - (-0.1), g.random()));
-  const double cost = __dadd_rn(1.0, u);
+  double cost = __dadd_rn(1.0, u);
+  if (!kUnit) cost = __dmul_rn(__dsqrt_rn(double(dx * dx + dy * dy)), cost);
   const bool no_fuel = s.fuel < cost;                                            // :288
   const bool water = w.passable(nx, ny);                                         // :293
   if (water) {                                                                   // :297-298
@@ -109,6 +113,11 @@ __device__ __forceinline__ int do_move(const WorldView& w, ShipR& s, G& g, int m
   done = no_fuel;
   return SHIPENV_ST_OK;
 }
+// m = 0..3 = N, E, S, W = (0,-1), (-1,0), (0,1), (1,0) (shipping/type.py:13-16)
+template <class G>
+__device__ __forceinline__ int do_move(const WorldView& w, ShipR& s, G& g, int m, double& reward, bool& done) {
+  return do_move_xy<true>(w, s, g, (m == 3) - (m == 1), (m == 2) - (m == 0), reward, done);
+}
 
 // step's dispatch (:359-376) with _select_port (:265-271), _take_cargo (:341-348), _take_fuel (:350-357).
 template <class G>
@@ -117,6 +126,7 @@ __device__ __forceinline__ int do_action(const WorldView& w, ShipR& s, G& g, int
   if (w.h->P == 0) return SHIPENV_ST_NO_PORTS;                                   // :360
   done = false;
   if (cat == kCatMove) return do_move(w, s, g, val, reward, done);
+  if (cat == kCatMoveXY) return do_move_xy<false>(w, s, g, val / 181 - 90, val % 181 - 90, reward, done);
   if (cat == kCatSelect) {
     if (val < 0 || val >= w.h->P) return SHIPENV_ST_SEL_RANGE;
     if (s.origin == val) return SHIPENV_ST_SEL_ORIGIN;
@@ -148,9 +158,11 @@ __device__ __forceinline__ void decode_action(int a, int P, int& cat, int& val) 
   }
   else if (a >= SHIPENV_ACT_EXT_CARGO && a < SHIPENV_ACT_EXT_FUEL) { cat = kCatCargo; val = a - SHIPENV_ACT_EXT_CARGO; }
   else if (a >= SHIPENV_ACT_EXT_FUEL && a < 0x8000) { cat = kCatFuel; val = a - SHIPENV_ACT_EXT_FUEL; }
+  else if (a <= SHIPENV_ACT_MOVE_XY_BASE && a >= SHIPENV_ACT_MOVE_XY_BASE - 181 * 181 + 1) { cat = kCatMoveXY; val = SHIPENV_ACT_MOVE_XY_BASE - a; }
 }
 __device__ __forceinline__ int encode_action(int cat, int val, int P) {
   if (cat == kCatMove) return val;
+  if (cat == kCatMoveXY) return SHIPENV_ACT_MOVE_XY_BASE - val;
   if (cat == kCatSelect) return 4 + val;
   if (cat == kCatCargo)
     return (val >= 0 && val < SHIPENV_N_CARGO_ACTIONS) ? 4 + P + val : SHIPENV_ACT_EXT_CARGO + val;

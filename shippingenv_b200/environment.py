@@ -11,8 +11,8 @@ The world (map + port table) is re-uploaded only when it changed.
 
 Differences from the reference, all documented in DESIGN.md: draws come from the Philox word
 stream (seeded from ``random`` at construction unless ``seed`` is given) instead of MT19937;
-moves must be one of the four unit moves; ``reset`` with fewer than two ports raises instead of
-looping forever; ``sample_action`` with ``fuel == 0`` at a port raises ``TypeError`` like the
+moves may be any integer pair with ``|dx|, |dy| <= 90`` (the int16 action code has no room for more); take amounts must
+be integral; ``reset`` with fewer than two ports raises instead of looping forever; ``sample_action`` with ``fuel == 0`` at a port raises ``TypeError`` like the
 reference does, but never consumes a draw.
 """
 import os
@@ -95,6 +95,9 @@ class Environment:
         self._io.done_bits, self._io.reset_bits, self._io.error_bits = self._ptr(_DONE), self._ptr(_RESET), self._ptr(_ERR)
         self._passable_key = None
         self._passable = None
+        self._rows = self._cols = 0      # shape of np_game as _sync_world last saw it
+        self._ragged = False             # size_game is not the grid's shape (non-square game_size)
+        self._sails = False              # set by _encode for a move outside ShipMove: its target is not ground
         self._w_game = self._w_ports = self._w_fuel = self._w_cargo = None   # what _sync_world last saw
 
     # ------------------------------------------------------------------ construction
@@ -131,10 +134,16 @@ class Environment:
         key = (self.np_game, len(self.port_positions))
         if self._passable_key is None or key[0] is not self._passable_key[0] or key[1] != self._passable_key[1]:
             g = np.asarray(self.np_game)
-            if g.ndim != 2 or g.shape[0] < self.size_game[0] or g.shape[1] < self.size_game[1]:
-                raise ValueError("np_game does not cover size_game (non-square maps are not supported)")
-            self._passable = np.ascontiguousarray(g[:self.size_game[0], :self.size_game[1]] != Entity.GROUND,
-                                                  dtype=np.uint8)
+            if g.ndim != 2:
+                raise ValueError("np_game must be a 2-D grid")
+            # Non-square game_size: cv2.resize makes the grid size_game[1] x size_game[0] while _is_within_map bounds
+            # x by size_game[0] and x indexes rows (:53, :99-100, :293).  The cells a ship can ever stand on are those
+            # inside both, which is what the device gets as its map; a move that passes _is_within_map but leaves the
+            # array raises numpy's IndexError in the reference, and in step() here before anything is launched.
+            self._rows, self._cols = int(g.shape[0]), int(g.shape[1])
+            wd, hd = min(int(self.size_game[0]), self._rows), min(int(self.size_game[1]), self._cols)
+            self._ragged = (wd, hd) != (int(self.size_game[0]), int(self.size_game[1]))
+            self._passable = np.ascontiguousarray(g[:wd, :hd] != Entity.GROUND, dtype=np.uint8)
             self._passable_bytes = self._passable.tobytes()
             self._passable_key = key
         ports = [(int(p[0]), int(p[1])) for p in self.port_positions]
@@ -267,10 +276,22 @@ class Environment:
                 raise ValueError("Move needs to be of format (x,y) or [x, y]")       # :274
             if self.destination_port_index is None:
                 raise Exception("Cannot move without destination port")               # :276
-            key = (int(value[0]), int(value[1]))
-            if key not in MOVE_INDEX:
-                raise NotImplementedError("only the four unit moves of ShipMove run on the device")
-            return MOVE_INDEX[key]
+            dx, dy = value
+            if not (isinstance(dx, (int, np.integer)) and isinstance(dy, (int, np.integer))):
+                self._float_move(dx, dy)
+            key = (int(dx), int(dy))
+            a = MOVE_INDEX.get(key)
+            if a is not None:
+                return a
+            # any other (dx, dy): _move_ship takes it as it is (:278-287).  Its checks that come before the first draw
+            # are made here: the bounds (:284) and -- for a non-square game_size -- numpy's own index check at :293.
+            nx, ny = self.ship_position[0] + key[0], self.ship_position[1] + key[1]
+            self._check_target(nx, ny)
+            if max(abs(key[0]), abs(key[1])) > nat.MOVE_XY_MAX:
+                raise NotImplementedError(f"moves of more than {nat.MOVE_XY_MAX} cells per axis have no action code")
+            # a move of (0, 0) onto water "moves" too (:295-304): fuel becomes a float, the cell is repainted
+            self._sails = self.np_game[nx, ny] != Entity.GROUND
+            return nat.ACT_MOVE_XY_BASE - ((key[0] + 90) * 181 + (key[1] + 90))
         if category == ActionType.SELECT_PORT:
             if not 0 <= value < P:
                 raise IndexError("Port index is out of range")                        # :269
@@ -284,6 +305,26 @@ class Environment:
             return 4 + P + nat.N_CARGO_ACTIONS + v if v < nat.N_FUEL_ACTIONS else nat.ACT_EXT_FUEL + v
         raise ValueError("Action category unknown")                                   # :374
 
+    def _check_target(self, nx, ny):
+        """What _move_ship checks about the target cell before its first draw (:284) and, when game_size is not the
+        shape of the grid cv2.resize made (:53), numpy's IndexError at :293 -- raised here before anything is launched
+        (the reference has drawn the fuel cost by then, but no state has changed and the cell starts over)."""
+        if not self._is_within_map(nx, ny):
+            raise ValueError("Move is out of range")                                  # :284
+        rows, cols = np.shape(self.np_game)
+        if nx >= rows:
+            raise IndexError(f"index {nx} is out of bounds for axis 0 with size {rows}")
+        if ny >= cols:
+            raise IndexError(f"index {ny} is out of bounds for axis 1 with size {cols}")
+
+    def _float_move(self, dx, dy):
+        """A move with a non-integer component: the reference gets as far as indexing np_game with a float (:293)."""
+        nx, ny = self.ship_position[0] + dx, self.ship_position[1] + dy
+        if not self._is_within_map(nx, ny):
+            raise ValueError("Move is out of range")                                  # :284
+        raise IndexError("only integers, slices (`:`), ellipsis (`...`), numpy.newaxis (`None`) and integer or "
+                         "boolean arrays are valid indices")
+
     def step(self, action):
         if len(self.port_positions) == 0:
             raise Exception("No ports available")                                     # :360
@@ -291,6 +332,11 @@ class Environment:
         ctx = self._sync_world()
         old = (int(self.ship_position[0]), int(self.ship_position[1])) if len(self.ship_position) == 2 else None
         fuel_was_int = isinstance(self.fuel, int)
+        free_move = a <= nat.ACT_MOVE_XY_BASE
+        if self._ragged and not free_move and action[0] == ActionType.MOVE_SHIP and old is not None:
+            dx, dy = MOVES[a]
+            if self._is_within_map(old[0] + dx, old[1] + dy):      # off-map moves are the device's to reject
+                self._check_target(old[0] + dx, old[1] + dy)
         self._pack(a)
         # the step and, with it, the draw of the sample_action() call that usually follows it
         if _USE_SERVER:
@@ -309,7 +355,7 @@ class Environment:
             raise exc(msg)
         self._clock = _U32.unpack_from(self._buf, _CLOCK)[0]
         self._word = 0
-        moved = (x, y) != old
+        moved = self._sails if free_move else (x, y) != old
         keep_int = fuel_was_int and not (action[0] == ActionType.MOVE_SHIP and moved)
         self._adopt(x, y, origin, dest, cargo, fuel, keep_int_fuel=keep_int)
         if moved:

@@ -42,8 +42,9 @@ def derive_grid(map_path, game_size=(100, 100)):
         img = cv2.resize(img, tuple(game_size), interpolation=cv2.INTER_AREA)
         _, grid = cv2.threshold(img, 128, 1, cv2.THRESH_BINARY)
     grid = np.asarray(grid).astype(int)
-    if ext in (".npy", ".npz") and tuple(grid.shape) != tuple(game_size):
-        raise ValueError(f"grid in {map_path} has shape {grid.shape}, expected {tuple(game_size)}")
+    # cv2.resize(img, (w, h)) returns h rows and w columns (:53): that is the shape a stored grid must have too
+    if ext in (".npy", ".npz") and tuple(grid.shape) != (game_size[1], game_size[0]):
+        raise ValueError(f"grid in {map_path} has shape {grid.shape}, expected {(game_size[1], game_size[0])}")
     _cache[key] = (stamp, grid)
     return grid.copy()
 

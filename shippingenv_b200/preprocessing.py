@@ -47,6 +47,18 @@ def map_action_to_env_action(agent_action, env):
     return [ActionType.TAKE_FUEL, agent_action - (N_MOVES + P + nat.N_CARGO_ACTIONS)]
 
 
+def move_action(dx, dy):
+    """Flat int16 action of MOVE_SHIP by (dx, dy) for the batched API: 0..3 for the four moves of ShipMove, the
+    SHIPENV_ACT_MOVE_XY code (include/shipenv.h) for any other pair with |dx|, |dy| <= 90 -- the reference's
+    _move_ship takes any pair (shipping/environment.py:278-287)."""
+    key = (int(dx), int(dy))
+    if key in MOVES:
+        return MOVES.index(key)
+    if max(abs(key[0]), abs(key[1])) > nat.MOVE_XY_MAX:
+        raise ValueError(f"moves of more than {nat.MOVE_XY_MAX} cells per axis have no action code")
+    return nat.ACT_MOVE_XY_BASE - ((key[0] + 90) * 181 + (key[1] + 90))
+
+
 def find_current_port_index(state):
     pos = tuple(state["ship"]["position"])
     for idx, port in enumerate(state["ports"]):

@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle.ref_harness import (RefBatch, import_reference, ref_rollout, f64_bits,  # noqa: E402
-                                NONE_PORT, POLICY, EXT_CARGO, EXT_FUEL)
+                                NONE_PORT, POLICY, EXT_CARGO, EXT_FUEL, move_xy)
 from oracle.philox_shim import PhiloxRandom  # noqa: E402
 
 SEED = 0x5EED
@@ -191,9 +191,157 @@ def discretize_golden(ns):
          keys=np.concatenate(keys))
 
 
+def free_moves_golden(ns):
+    """g13: MOVE_SHIP with moves outside ShipMove -- the reference's _move_ship takes any (dx, dy)
+    (shipping/environment.py:278-287): fuel cost sqrt(dx^2+dy^2) * (1 + uniform), terrain of the target cell only,
+    closer/farther on the real distances (ties count as farther).  Includes (0, 0), the four unit moves written
+    as pairs, jumps over land, off-map targets, and crafted states (a null move on the destination port, negative
+    fuel, a jump onto the destination with cargo)."""
+    PORTS = ns.consts.DEFAULT_PORTS
+    rng = np.random.default_rng(1313)
+    T, N = 320, 64
+    b = RefBatch(ns, N, SEED + 13, PORTS, STOCK_FUEL, STOCK_CARGO, env_id_base=77)
+    b.reset()
+    crafted = [(60, 22, 4, 1, 7, 150.0), (60, 22, 4, 1, 0, -2.5), (57, 26, 4, 1, 9, 99.5), (62, 72, 4, 1, 3, 0.4),
+               (0, 0, 4, 1, 0, 200), (99, 99, 0, 2, 55, 200)]
+    for i, c in enumerate(crafted):
+        b.set_state(i, *c)
+    first = [move_xy(0, 0), move_xy(0, 0), move_xy(3, -4), move_xy(-1, 0), move_xy(90, 90), move_xy(-90, -90)]
+    kind = rng.random((T, N))
+    small = np.vectorize(move_xy)(rng.integers(-3, 4, (T, N)), rng.integers(-3, 4, (T, N)))
+    medium = np.vectorize(move_xy)(rng.integers(-12, 13, (T, N)), rng.integers(-12, 13, (T, N)))
+    large = np.vectorize(move_xy)(rng.integers(-90, 91, (T, N)), rng.integers(-90, 91, (T, N)))
+    acts = rng.integers(0, 4, (T, N))
+    acts = np.where(kind > 0.25, small, acts)
+    acts = np.where(kind > 0.80, medium, acts)
+    acts = np.where(kind > 0.95, large, acts)
+    acts[0, :len(first)] = first
+    acts[1, :len(first)] = first[::-1]
+    tr = run(b, acts, 120, True)
+    xy = acts <= -2
+    print("  free moves: accepted =", int(((tr["status"] == 0) & xy).sum()), " off-map =", int(((tr["status"] == 1) & xy).sum()),
+          " arrivals =", int((tr["reward"] > 5).sum()), " dones =", int(tr["done"].sum()), " resets =", int(tr["reset"].sum()))
+    save("g13_free_moves", **tr, **port_meta(b))
+
+
+def facade_trace_golden(ns):
+    """g14: the reference's single-env API driven call by call -- Environment(map, game_size), add_port, reset,
+    step([category, value]) -- on the default map with moves of any (dx, dy) (lists, tuples, numpy integers, (0, 0),
+    a float component, a triple) and on NON-SQUARE game sizes, where cv2.resize makes the grid size_game[1] x
+    size_game[0] while _is_within_map bounds x by size_game[0] (shipping/environment.py:53, :99-100): moves that pass
+    the bounds check but leave the array raise numpy's IndexError at :293.  Per call the trace holds the exception
+    (class name + message) or the new attributes, the reward bits, done, and a hash of np_game (the paint).
+    The shim is positioned the way the facade draws: cell (env id, clock), clock + 1 per accepted step, reset draws
+    from the current cell and moves the clock to the next episode."""
+    AT = ns.envmod.ActionType
+    out = {}
+    scenarios = [("sq", (100, 100), 5, 260), ("wide", (120, 80), 4, 260), ("tall", (80, 120), 4, 260)]
+    for tag, size, n_ports, T in scenarios:
+        rng = np.random.default_rng(1400 + len(tag) + size[0])
+        shim = PhiloxRandom(SEED + 14)
+        ns.envmod.random = shim
+        env_id = 5 + size[0]
+        e = ns.envmod.Environment(ns.map_path, size)
+        out[f"{tag}_grid"] = e.np_game.astype(np.uint8)
+        out[f"{tag}_size"] = np.array(size, np.int64)
+        lim = min(size)
+        if tag == "sq":
+            ports = [list(p) for p in ns.consts.DEFAULT_PORTS]
+        else:      # ports on water cells of the part of the grid a ship can reach, spread out
+            cand = [(x, y) for x in range(4, lim - 4) for y in range(4, lim - 4)
+                    if e.np_game[x, y] != 0 and e.np_game[x - 1, y] != 0 and e.np_game[x + 1, y] != 0]
+            ports = [list(map(int, cand[k])) for k in rng.choice(len(cand), n_ports, replace=False)]
+        for k, p in enumerate(ports):
+            shim.seek_port(k)
+            e.add_port(list(p))
+        out[f"{tag}_ports"] = np.array(ports, np.int64)
+        out[f"{tag}_env_id"] = np.int64(env_id)
+        clock = 0
+        rec = dict(kind=[], cat=[], v0=[], v1=[], exc=[], state=[], fuel=[], reward=[], done=[], grid=[])
+
+        def snap(kind, cat, v0, v1, exc, reward, done):
+            pos = e.ship_position if len(e.ship_position) == 2 else [255, 255]
+            o = NONE_PORT if e.origin_port_index is None else e.origin_port_index
+            d = NONE_PORT if e.destination_port_index is None else e.destination_port_index
+            rec["kind"].append(kind); rec["cat"].append(cat); rec["v0"].append(v0); rec["v1"].append(v1)
+            rec["exc"].append(exc)
+            rec["state"].append([int(pos[0]), int(pos[1]), o, d, int(e.cargo), int(isinstance(e.fuel, int))])
+            rec["fuel"].append(f64_bits(e.fuel)); rec["reward"].append(f64_bits(reward)); rec["done"].append(int(done))
+            rec["grid"].append(int.from_bytes(hashlib.sha256(e.np_game.astype(np.uint8).tobytes()).digest()[:8], "little"))
+
+        def do_reset():
+            nonlocal clock
+            shim.seek_env(env_id, clock)
+            e.reset()
+            clock = ((clock >> 16) + 1) << 16
+            snap(0, 0, 0, 0, "", 0.0, 0)
+
+        def do_step(cat, value, kind=1):
+            nonlocal clock
+            shim.seek_env(env_id, clock)
+            v0, v1 = (value[0], value[1]) if cat == AT.MOVE_SHIP and len(value) == 2 else (value if cat != AT.MOVE_SHIP else 0, 0)
+            try:
+                _, r, d, _ = e.step([cat, value])
+            except Exception as exc:
+                snap(kind, cat, v0, v1, f"{type(exc).__name__}|{exc}", 0.0, 0)
+                return
+            clock += 1
+            snap(kind, cat, v0, v1, "", r, d)
+
+        do_reset()
+        # kinds: 1 list move, 2 tuple move, 3 numpy-integer move, 4 float component, 5 triple
+        do_step(AT.MOVE_SHIP, [0, 0]); do_step(AT.MOVE_SHIP, (0, 0), 2)
+        do_step(AT.MOVE_SHIP, [0.5, 0], 4); do_step(AT.MOVE_SHIP, [200.5, 0], 4); do_step(AT.MOVE_SHIP, [1, 0, 0], 5)
+        do_step(AT.MOVE_SHIP, [-200, 3]); do_step(AT.MOVE_SHIP, [np.int64(1), np.int64(-1)], 3)
+        for t in range(T):
+            cur = e._get_current_port_idx()
+            u = rng.random()
+            if cur is not None and e.cargo == 0 and u < 0.7:
+                do_step(AT.TAKE_CARGO, int(rng.integers(1, e.port_cargo[cur] + 1)))
+            elif u < 0.04:
+                do_reset()
+            elif u < 0.10:
+                do_step(AT.SELECT_PORT, int(rng.integers(0, len(ports) + 1)))
+            else:
+                tx, ty = e.port_positions[e.destination_port_index]
+                x, y = e.ship_position
+                if u < 0.55:       # towards the destination, a few cells at a time (may jump over land)
+                    dx = int(np.clip(tx - x, -3, 3)) + int(rng.integers(-1, 2))
+                    dy = int(np.clip(ty - y, -3, 3)) + int(rng.integers(-1, 2))
+                elif u < 0.85:     # anywhere nearby
+                    dx, dy = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
+                else:              # far: off the map, or (non-square) inside size_game but outside the grid
+                    dx, dy = int(rng.integers(-60, 61)), int(rng.integers(-60, 61))
+                    if tag == "wide" and u > 0.93:
+                        dx = int(rng.integers(80, 120)) - x
+                    if tag == "tall" and u > 0.93:
+                        dy = int(rng.integers(80, 120)) - y
+                kind = 1 + int(rng.integers(0, 3))
+                value = [dx, dy] if kind == 1 else (dx, dy) if kind == 2 else [np.int64(dx), np.int64(dy)]
+                do_step(AT.MOVE_SHIP, value, kind)
+        excs = [x.split("|")[0] for x in rec["exc"] if x]
+        print(f"  facade trace {tag} {size}: calls {len(rec['kind'])}, exceptions {dict(collections.Counter(excs))}, "
+              f"arrivals {sum(1 for r in rec['reward'] if np.array(r, np.uint64).view(np.float64) > 5)}")
+        for k in ("kind", "cat", "v1", "done"):
+            out[f"{tag}_{k}"] = np.array(rec[k], np.int64)
+        out[f"{tag}_v0"] = np.array([float(v) for v in rec["v0"]], np.float64)
+        out[f"{tag}_state"] = np.array(rec["state"], np.int64)
+        for k, name in (("fuel", "fuel"), ("reward", "reward"), ("grid", "paint")):
+            out[f"{tag}_{name}"] = np.array(rec[k], np.uint64)
+        out[f"{tag}_exc"] = np.array(rec["exc"])
+    out["seed"] = np.uint64(SEED + 14)
+    save("g14_facade_trace", **out)
+
+
 def main():
     ns = import_reference()
     PORTS = ns.consts.DEFAULT_PORTS
+    if "free_moves" in sys.argv[1:]:
+        free_moves_golden(ns)
+        return
+    if "facade_trace" in sys.argv[1:]:
+        facade_trace_golden(ns)
+        return
     if "valid" in sys.argv[1:]:
         valid_action_golden(ns)
         return
@@ -407,6 +555,8 @@ def main():
     valid_action_golden(ns)
     discretize_golden(ns)
     mcts_golden(ns)
+    free_moves_golden(ns)
+    facade_trace_golden(ns)
 
 
 if __name__ == "__main__":

@@ -189,7 +189,7 @@ def test_step_many_equals_repeated_step(torch_cuda, default_map, n, T, policy):
     assert g_ships.tobytes() == ref.ships.tobytes() and (g_clock == ref.clock).all()
 
 
-@pytest.mark.parametrize("name", ["g1_moves", "g2_policy", "g3_mixed"])
+@pytest.mark.parametrize("name", ["g1_moves", "g2_policy", "g3_mixed", "g13_free_moves"])
 def test_step_many_replays_reference_traces(torch_cuda, name):
     """The reference-generated fixtures (moves, policy, the whole flat action space) through shipenv_step_many in one
     launch: final ships, per-step reward bits and status as recorded from the reference."""

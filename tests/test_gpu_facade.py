@@ -105,6 +105,14 @@ def test_facade_paints_np_game_like_the_reference():
     assert replay_paint_trace() == 4 * 700
 
 
+def test_facade_free_moves_and_nonsquare_maps_like_the_reference():
+    """g14: moves of any (dx, dy) and non-square game sizes through the facade on the real kernels (the served step and,
+    with SHIPENV_NO_SERVER semantics, the launch path are the same general transition): exception class + message or
+    attributes, reward bits, done and np_game paint after each of 804 calls of the reference's API."""
+    from facade_trace import replay_facade_trace
+    assert replay_facade_trace() == 804
+
+
 def test_facade_crafted_states_and_policy_loop():
     """g6: attributes assigned from outside (as agents/mcts.py:199-208 does), then the reference's
     `a = sample_action(); try: step(a) except: continue` loop for policy rows."""

@@ -12,7 +12,10 @@ pytestmark = pytest.mark.gpu
 FUEL_EDGES = np.array([0.0, -0.0, 0.5, 0.9, 0.95, 1.0, 1.05, 1.1, 1.1000000000000001, 200.0, -3.5, 1e-300, 1e6,
                        0.8999999999999999, 5e-324, 1e15], np.float64)
 ACTION_EDGES = np.array([-1, -1, -1, 0, 1, 2, 3, 4, 8, 9, 10, 29, 58, 59, 60, 75, 258, 259, 260, -2, -32768, 32767,
-                         0x4000, 0x4001, 0x4014, 0x5FFF, 0x6000, 0x6001, 0x6010, 0x7FFF, 0x3FFF], np.int64)
+                         0x4000, 0x4001, 0x4014, 0x5FFF, 0x6000, 0x6001, 0x6010, 0x7FFF, 0x3FFF,
+                         # moves by any (dx, dy): -2 - ((dx+90)*181 + (dy+90)); -32762 is the last code, -32763 is junk
+                         -2 - (90 * 181 + 90), -2 - (91 * 181 + 91), -2 - (87 * 181 + 92), -2 - (95 * 181 + 83),
+                         -2 - (90 * 181 + 89), -2 - (102 * 181 + 90), -32762, -32763, -3], np.int64)
 
 
 def random_population(rng, n, passable, ports):

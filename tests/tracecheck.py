@@ -81,4 +81,4 @@ def replay(z, stepper):
 
 
 TRACES = ["g1_moves", "g2_policy", "g3_mixed", "g4_navigator", "g5_edges_moves", "g5_edges_policy",
-          "g6_crafted", "g7_word0"]
+          "g6_crafted", "g7_word0", "g13_free_moves"]
