@@ -29,18 +29,20 @@ __device__ __forceinline__ int rollout_attempt(const WorldView& w, ShipR& s, G& 
   const uint32_t* const win = g.window();              // the next words of the stream: win[k * stride]
   constexpr uint32_t kS = G::kColumnStride;
   const uint32_t w0 = win[0];
-  if (on_port) {                                       // sample_action looks at the port first (:247-260)
-    if (s.cargo != 0) {
-      if (s.fuel == 0.0) return 2;                     // :258-260 -> :163
-    } else {                                           // TAKE_CARGO randint(1, stock) (:255-257, :341-348)
-      const int stock = int(w.h->port[current_port(w, s)] >> 24);
-      if (stock == 0) return 2;                        // randint(1, 0): the general code rejects it
-      s.cargo += 1 + int(__umulhi(w0, uint32_t(stock)));
-      reward = w.h->r_take_cargo;
-      done = false;
-      g.advance(1);
-      return 0;
-    }
+  // sample_action looks at the port first (:247-260).  ONE test decides whether a lane leaves the straight-line code:
+  // written as nested ifs (on a port -> cargo != 0 -> fuel == 0) the lanes that sit on a port with cargo on board
+  // reached the MOVE code below on a path of their own, and the warp ran all of it twice (ncu, round 2: 1.3 passes
+  // of 24 lanes per loop iteration on BASELINE configs[3] roots, where ships linger around their land-locked ports).
+  if (on_port && (s.cargo == 0 || s.fuel == 0.0)) {
+    if (s.cargo != 0) return 2;                        // fuel == 0 with cargo on board: :258-260 -> :163
+    // TAKE_CARGO randint(1, stock) (:255-257, :341-348)
+    const int stock = int(w.h->port[current_port(w, s)] >> 24);
+    if (stock == 0) return 2;                          // randint(1, 0): the general code rejects it
+    s.cargo += 1 + int(__umulhi(w0, uint32_t(stock)));
+    reward = w.h->r_take_cargo;
+    done = false;
+    g.advance(1);
+    return 0;
   }
   const int m = int(__umulhi(w0, 4u));                 // choice([N, E, S, W]) (:165-167)
   const int dx = (m & 1) * (m - 2), dy = ((m & 1) ^ 1) * (m - 1);
