@@ -117,7 +117,7 @@ struct RngFifo {
   }
   __device__ __forceinline__ void refill() {
     uint32_t w[4];
-    philox4x32_10(filled >> 2, c1, c2, c3, rk[0], rk[1], w);
+    philox_rk(filled >> 2, c1, c2, c3, rk, w);                   // round keys from the kernel parameters
     uint32_t* p = slot + (filled & (kRing - 1u)) * kStride;      // 0, 4, 8 or 12
 #pragma unroll
     for (int k = 0; k < 4; ++k) { p[k * kStride] = w[k]; p[(k + kRing) * kStride] = w[k]; }
