@@ -185,11 +185,13 @@ struct MctsTree {
   double mean[kNodes];          // total / visits as of the last backpropagation through the node (UCB1's first term)
   uint8_t visits[kNodes];       // <= S <= 126
   uint8_t parent[kNodes];
-  uint8_t info[kNodes];         // action (2 bits) | nchild << 2 (3 bits) | moves_ok << 5
-  uint8_t child[kNodes][4];
+  uint8_t info[kNodes];         // action (2 bits) | tried actions << 2 (4 bits: the children's actions) | moves_ok << 6
+  alignas(4) uint8_t child[kNodes][4];   // in expansion order; read as one word
   __device__ __forceinline__ int action(int n) const { return info[n] & 3; }
-  __device__ __forceinline__ int nchild(int n) const { return (info[n] >> 2) & 7; }
-  __device__ __forceinline__ bool moves_ok(int n) const { return info[n] & 32; }
+  __device__ __forceinline__ uint32_t tried(int n) const { return (info[n] >> 2) & 15u; }
+  __device__ __forceinline__ int nchild(int n) const { return __popc(tried(n)); }
+  __device__ __forceinline__ bool moves_ok(int n) const { return info[n] & 64; }
+  __device__ __forceinline__ uint32_t children(int n) const { return *reinterpret_cast<const uint32_t*>(child[n]); }
 };
 
 // get_possible_actions (:50-89) is the four moves iff a destination is set and not (fuel == 0 with an origin)
@@ -203,22 +205,36 @@ __device__ __forceinline__ bool mcts_moves_ok(const ShipR& s) {
 // the first term is cached per node when its statistics change (backpropagation), the second depends on the two
 // visit counts only and comes from a table built once per CTA with the same operations,
 // explore[N * (N + 1) / 2 + n] for 1 <= n <= N <= S + 1 (null: S too large for the table, computed in place).
-template <int kNodes>
+// kFull: the node has all four children (the only case selection meets, :261): the loop is unrolled, so the four
+// children's statistics are fetched side by side -- the tree lives in local memory, and a loop over a run-time child
+// count made every level of the descent eight dependent L2 round trips (child index -> visits / mean, four times).
+template <int kNodes, bool kFull>
 __device__ __forceinline__ int mcts_best_child(const MctsTree<kNodes>& t, int node, double c_param, const double* log_table,
                                                const double* explore) {
   int best = 0;
   double best_v = 0.0;
   const int N = t.visits[node];
+  const uint32_t kids = t.children(node);
   const double two_log = __dmul_rn(2.0, log_table[N]);
-  const int nc = t.nchild(node);
-  for (int k = 0; k < nc; ++k) {
-    const int ch = t.child[node][k];
-    const int n = t.visits[ch];
+  const int nc = kFull ? 4 : t.nchild(node);
+  int n_k[4];
+  double mean_k[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ch = (kids >> (8 * k)) & 255u;
+    const bool has = kFull || k < nc;
+    n_k[k] = has ? t.visits[ch] : 0;
+    mean_k[k] = has ? t.mean[ch] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (!kFull && k >= nc) break;
+    const int n = n_k[k];
     double v;
     if (n == 0) v = __longlong_as_double(0x7FF0000000000000LL);
-    else if (explore && n <= N) v = __dadd_rn(t.mean[ch], c_param == 0.0 ? 0.0 : explore[N * (N + 1) / 2 + n]);
-    else v = __dadd_rn(t.mean[ch], __dmul_rn(c_param, __dsqrt_rn(__ddiv_rn(two_log, double(n)))));
-    if (k == 0 || v > best_v) { best = ch; best_v = v; }
+    else if (explore && n <= N) v = __dadd_rn(mean_k[k], c_param == 0.0 ? 0.0 : explore[N * (N + 1) / 2 + n]);
+    else v = __dadd_rn(mean_k[k], __dmul_rn(c_param, __dsqrt_rn(__ddiv_rn(two_log, double(n)))));
+    if (k == 0 || v > best_v) { best = int((kids >> (8 * k)) & 255u); best_v = v; }
   }
   return best;
 }
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
     MctsTree<kNodes> t;
     int n_nodes = 1, st = SHIPENV_ST_OK;
     t.total[0] = 0.0; t.mean[0] = 0.0; t.visits[0] = 0; t.parent[0] = 255;
-    t.info[0] = uint8_t(mcts_moves_ok(root) ? 32 : 0);
+    t.info[0] = uint8_t(mcts_moves_ok(root) ? 64 : 0);
     for (int sim = 0; sim < a.S && st == SHIPENV_ST_OK; ++sim) {
       ShipR s = root;                                                        // _create_env_copy, :257
       RngFifo<kMctsThreads> g;
@@ -260,18 +276,17 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
       double rew = 0.0;
       for (;;) {                                                             // selection, :260-268
         if (!t.moves_ok(node)) { st = SHIPENV_ST_MCTS_UNSUPPORTED; break; }
-        if (t.nchild(node) != 4) break;
+        if (t.tried(node) != 15u) break;
         g.ensure();
-        node = mcts_best_child(t, node, a.c_param, log_table, explore);
+        node = mcts_best_child<kNodes, true>(t, node, a.c_param, log_table, explore);
         const int e = do_action(w, s, g, kCatMove, t.action(node), rew, done);
         if (e != SHIPENV_ST_OK || done) break;
       }
       if (st != SHIPENV_ST_OK) break;
       // expansion, :271-279: untried actions in the order N, S, E, W (:80-87) = flat indices 0, 2, 1, 3
-      uint32_t tried = 0;
-      const int nc = t.nchild(node);
-      for (int k = 0; k < nc; ++k) tried |= 1u << t.action(t.child[node][k]);
-      const int n_un = 4 - __popc(tried);
+      const uint32_t tried = t.tried(node);
+      const int nc = __popc(tried);
+      const int n_un = 4 - nc;
       if (n_un > 0) {
         g.ensure();
         int pick = g.below(n_un), act = 0;                                   // random.choice(untried), :274
@@ -283,9 +298,9 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
         if (e != SHIPENV_ST_OK) continue;                                    // :278-279: the simulation is skipped
         const int ch = n_nodes++;
         t.total[ch] = rew; t.mean[ch] = 0.0; t.visits[ch] = 0; t.parent[ch] = uint8_t(node);   // :144-146
-        t.info[ch] = uint8_t(act | (mcts_moves_ok(s) ? 32 : 0));
+        t.info[ch] = uint8_t(act | (mcts_moves_ok(s) ? 64 : 0));
         t.child[node][nc] = uint8_t(ch);
-        t.info[node] = uint8_t(t.info[node] + 4);                            // one more child
+        t.info[node] = uint8_t(t.info[node] | (4u << act));                  // one more child: its action is tried
         node = ch;
       }
       // simulation: _rollout, :211-238, continuing the same word stream
@@ -311,7 +326,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
     int act = -1;
     if (st == SHIPENV_ST_OK) {
       if (nc0 == 0) st = SHIPENV_ST_MCTS_NO_CHILDREN;                        // :291-292
-      else act = t.action(mcts_best_child(t, 0, 0.0, log_table, explore));   // :288-290
+      else act = t.action(mcts_best_child<kNodes, false>(t, 0, 0.0, log_table, explore));   // :288-290
     }
     a.action[r] = int16_t(act);
     a.status[r] = uint8_t(st);
