@@ -21,11 +21,21 @@ namespace shipenv {
 // Returns 0 = step accepted, 1 = rejected (the draw is consumed, the agents' loop tries again),
 //         2 = not handled here, nothing consumed.
 // ------------------------------------------------------------------------------------------
+// The header fields every step looks at, read once per thread: the word FIFO is written in the loop, so the compiler
+// must assume the staged world may have changed and would otherwise re-read them from shared memory every step, at the
+// head of the step's dependency chains (bounds test, bitmap address).
+struct RollHdr {
+  int W, H, cap, wpr, nbw, P;
+  double p_loss;
+  __device__ __forceinline__ explicit RollHdr(const WorldView& w)
+      : W(w.h->W), H(w.h->H), cap(w.h->capacity), wpr(w.h->wpr), nbw(w.h->n_bit_words), P(w.h->P), p_loss(w.h->p_loss) {}
+};
+
 template <class G>
-__device__ __forceinline__ int rollout_attempt(const WorldView& w, ShipR& s, G& g, double& reward, bool& done) {
-  const int W = w.h->W, H = w.h->H, cap = w.h->capacity;
+__device__ __forceinline__ int rollout_attempt(const WorldView& w, const RollHdr& k, ShipR& s, G& g, double& reward, bool& done) {
+  const int W = k.W, H = k.H, cap = k.cap;
   if (s.dest == kNone || s.cargo < 0 || unsigned(s.x) >= unsigned(W) || unsigned(s.y) >= unsigned(H)) return 2;
-  const bool on_port = w.port_cell(s.x, s.y);
+  const bool on_port = (w.bits[k.nbw + s.x * k.wpr + (s.y >> 5)] >> (s.y & 31)) & 1u;
   const uint32_t* const win = g.window();              // the next words of the stream: win[k * stride]
   constexpr uint32_t kS = G::kColumnStride;
   const uint32_t w0 = win[0];
@@ -51,7 +61,7 @@ __device__ __forceinline__ int rollout_attempt(const WorldView& w, ShipR& s, G& 
   const uint32_t w1 = win[kS], w2 = win[2 * kS], w3 = win[3 * kS], w4 = win[4 * kS], w5 = win[5 * kS], w6 = win[6 * kS];
   const double cost = __dadd_rn(1.0, __dadd_rn(-0.1, __dmul_rn(0.1 - (-0.1), unit_double(w1))));   // :287, :103-104
   const bool no_fuel = s.fuel < cost;                                                   // :288
-  const bool water = w.passable(nx, ny);                                                // :293
+  const bool water = (w.bits[nx * k.wpr + (ny >> 5)] >> (ny & 31)) & 1u;                // :293
   const uint32_t pd = w.h->port[s.dest];
   const int tx = pd & 255u, ty = (pd >> 8) & 255u;
   const bool closer = (s.x - tx) * dx + (s.y - ty) * dy < 0;                            // :307-315, unit move
@@ -66,7 +76,7 @@ __device__ __forceinline__ int rollout_attempt(const WorldView& w, ShipR& s, G& 
   const int part = __double2int_rz(__dmul_rn(unit_double(med), double(s.cargo)));
   const bool has_cargo = s.cargo != 0;
   const int loss = (!has_cargo || lose_none) ? 0 : lose_all ? s.cargo : part;
-  const double r_loss = __dadd_rn(r, __dmul_rn(double(loss), w.h->p_loss));
+  const double r_loss = __dadd_rn(r, __dmul_rn(double(loss), k.p_loss));
   r = trigger ? r_loss : r;
   s.cargo -= trigger ? loss : 0;
   g.advance(3u + (trigger ? 1u : 0u) + ((trigger && has_cargo && !lose_none && !lose_all) ? 3u : 0u));
@@ -88,7 +98,7 @@ __device__ __forceinline__ int rollout_attempt(const WorldView& w, ShipR& s, G& 
 // MCTSAgent._rollout (agents/mcts.py:211-238) from ship s on stream g: at most L accepted steps.
 // Returns the status (SHIPENV_ST_OK unless the rollout had to stop); total / steps by reference.
 template <class G>
-__device__ __forceinline__ int rollout_run(const WorldView& w, ShipR& s, G& g, int L, double& total, int& steps) {
+__device__ __forceinline__ int rollout_run(const WorldView& w, const RollHdr& k, ShipR& s, G& g, int L, double& total, int& steps) {
   total = 0.0;                                     // agents/mcts.py:224
   steps = 0;
   bool done = false;
@@ -97,7 +107,7 @@ __device__ __forceinline__ int rollout_run(const WorldView& w, ShipR& s, G& g, i
     g.top_up();
     g.ensure(7);
     double reward = 0.0;
-    int rc = w.h->P == 0 ? 2 : rollout_attempt(w, s, g, reward, done);
+    int rc = k.P == 0 ? 2 : rollout_attempt(w, k, s, g, reward, done);
     if (rc == 2) {                                 // the general code: every state the reference can be in
       if (w.h->P == 0) return SHIPENV_ST_NO_PORTS;
       if (s.dest == kNone && current_port(w, s) < 0) return SHIPENV_ST_NO_DEST;
@@ -142,6 +152,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
   uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + ((a.world_bytes + 127u) & ~127u));   // [32][blockDim.x] words
   const int64_t total = a.R * int64_t(a.S);
   const int64_t n_tiles = (total + kRolloutThreads - 1) / kRolloutThreads;
+  const RollHdr hdr(w);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t j = tile * kRolloutThreads + threadIdx.x;
     if (j >= total) continue;
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
     g.seek(a.round_key, fifo + threadIdx.x, uint32_t(sim), a.root_id_base + uint64_t(r));
     double total_reward;
     int steps;
-    const int st = rollout_run(w, s, g, a.L, total_reward, steps);
+    const int st = rollout_run(w, hdr, s, g, a.L, total_reward, steps);
     a.returns[j] = total_reward;
     if (a.final) a.final[j] = pack(s);
     if (a.steps) a.steps[j] = steps;
@@ -261,6 +272,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
     }
   }
   __syncthreads();
+  const RollHdr hdr(w);
   for (int64_t r = blockIdx.x * int64_t(kMctsThreads) + threadIdx.x; r < a.R; r += int64_t(gridDim.x) * kMctsThreads) {
     const ShipR root = unpack(__ldg(a.roots + r));
     MctsTree<kNodes> t;
@@ -306,7 +318,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
       // simulation: _rollout, :211-238, continuing the same word stream
       double total;
       int steps;
-      st = rollout_run(w, s, g, a.L, total, steps);
+      st = rollout_run(w, hdr, s, g, a.L, total, steps);
       if (st != SHIPENV_ST_OK) break;
       for (int n = node; n != 255; n = t.parent[n]) {                        // :149-159
         t.visits[n] += 1;
