@@ -284,12 +284,16 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
       RngFifo<kMctsThreads> g;
       g.seek(a.round_key, fifo + threadIdx.x, uint32_t(sim), a.root_id_base + uint64_t(r));
       int node = 0;
+      // the last nodes of the descent, leaf first (255 = none): backpropagation then knows its first levels without
+      // walking the parent links, and fetches their statistics side by side
+      int up1 = 255, up2 = 255, up3 = 255;
       bool done = false;
       double rew = 0.0;
       for (;;) {                                                             // selection, :260-268
         if (!t.moves_ok(node)) { st = SHIPENV_ST_MCTS_UNSUPPORTED; break; }
         if (t.tried(node) != 15u) break;
         g.ensure();
+        up3 = up2; up2 = up1; up1 = node;
         node = mcts_best_child<kNodes, true>(t, node, a.c_param, log_table, explore);
         const int e = do_action(w, s, g, kCatMove, t.action(node), rew, done);
         if (e != SHIPENV_ST_OK || done) break;
@@ -313,6 +317,7 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
         t.info[ch] = uint8_t(act | (mcts_moves_ok(s) ? 64 : 0));
         t.child[node][nc] = uint8_t(ch);
         t.info[node] = uint8_t(t.info[node] | (4u << act));                  // one more child: its action is tried
+        up3 = up2; up2 = up1; up1 = node;
         node = ch;
       }
       // simulation: _rollout, :211-238, continuing the same word stream
@@ -320,10 +325,31 @@ __global__ void __launch_bounds__(kMctsThreads) mcts_kernel(const __grid_constan
       int steps;
       st = rollout_run(w, hdr, s, g, a.L, total, steps);
       if (st != SHIPENV_ST_OK) break;
-      for (int n = node; n != 255; n = t.parent[n]) {                        // :149-159
-        t.visits[n] += 1;
-        t.total[n] = __dadd_rn(t.total[n], total);
-        t.mean[n] = __ddiv_rn(t.total[n], double(t.visits[n]));
+      {                                                                      // backpropagate, :149-159
+        const int path[4] = {node, up1, up2, up3};
+        int v_k[4];
+        double t_k[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                  // four levels' statistics in one round trip
+          const int n = path[k] == 255 ? 0 : path[k];
+          v_k[k] = t.visits[n];
+          t_k[k] = t.total[n];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (path[k] != 255) {
+            const int n = path[k];
+            const double tt = __dadd_rn(t_k[k], total);
+            t.visits[n] = uint8_t(v_k[k] + 1);
+            t.total[n] = tt;
+            t.mean[n] = __ddiv_rn(tt, double(v_k[k] + 1));
+          }
+        }
+        for (int n = up3 == 255 ? 255 : t.parent[up3]; n != 255; n = t.parent[n]) {   // deeper trees: the parent links
+          t.visits[n] += 1;
+          t.total[n] = __dadd_rn(t.total[n], total);
+          t.mean[n] = __ddiv_rn(t.total[n], double(t.visits[n]));
+        }
       }
     }
     const int nc0 = t.nchild(0);

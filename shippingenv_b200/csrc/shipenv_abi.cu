@@ -115,7 +115,7 @@ struct shipenv_ctx {
   bool no_fast_kernel = false;   // SHIPENV_NO_FAST=1: route every step through step_kernel (A/B testing)
   // cached occupancy (resident CTAs per SM) per kernel, keyed by dynamic smem size
   struct Occ { size_t smem = ~size_t(0); int blocks = 0; };
-  Occ occ_fast[8], occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_step_sample, occ_rollout, occ_valid, occ_mcts[2], occ_many[6];
+  Occ occ_fast[8], occ_step, occ_step_full, occ_step_obs, occ_step_obs_full, occ_reset, occ_observe, occ_sample, occ_step_sample, occ_rollout, occ_valid, occ_mcts[3], occ_many[6];
 };
 
 namespace {
@@ -931,10 +931,12 @@ int shipenv_mcts(shipenv_ctx* c, const shipenv_ship* roots, int64_t R, int S, in
   const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + RngFifo<kMctsThreads>::kWords * 4 * kMctsThreads +
                       sizeof(double) * (SHIPENV_MCTS_MAX_SIMS + 2) +
                       (a.explore_table ? sizeof(double) * size_t(S + 2) * size_t(S + 3) / 2 : 0);
-  const bool small_tree = S + 2 <= 64;               // one node per simulation plus the root
-  void (*kernel)(const MctsArgs) = small_tree ? mcts_kernel<64> : mcts_kernel<128>;
+  // one node per simulation plus the root: the tree is a per-thread array in local memory, and the smaller its
+  // footprint the more of it stays in L1 (52 nodes = the reference's 50 simulations)
+  const int tree = S + 2 <= 52 ? 0 : S + 2 <= 64 ? 1 : 2;
+  void (*kernel)(const MctsArgs) = tree == 0 ? mcts_kernel<52> : tree == 1 ? mcts_kernel<64> : mcts_kernel<128>;
   int grid = 0;
-  if (int rc = grid_for(c, kernel, c->occ_mcts[small_tree ? 0 : 1], kMctsThreads, smem, (R + kMctsThreads - 1) / kMctsThreads, &grid)) return rc;
+  if (int rc = grid_for(c, kernel, c->occ_mcts[tree], kMctsThreads, smem, (R + kMctsThreads - 1) / kMctsThreads, &grid)) return rc;
   kernel<<<grid, kMctsThreads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   ++g_launches;
