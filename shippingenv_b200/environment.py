@@ -11,8 +11,9 @@ The world (map + port table) is re-uploaded only when it changed.
 
 Differences from the reference, all documented in DESIGN.md: draws come from the Philox word
 stream (seeded from ``random`` at construction unless ``seed`` is given) instead of MT19937;
-moves may be any integer pair with ``|dx|, |dy| <= 90`` (the int16 action code has no room for more); take amounts must
-be integral; ``reset`` with fewer than two ports raises instead of looping forever; ``sample_action`` with ``fuel == 0`` at a port raises ``TypeError`` like the
+moves may be any integer pair with ``|dx|, |dy| <= 90`` (the int16 action code has no room for
+more); take amounts must be integral; ``reset`` with fewer than two ports raises instead of
+looping forever; ``sample_action`` with ``fuel == 0`` at a port raises ``TypeError`` like the
 reference does, but never consumes a draw.
 """
 import os
@@ -95,7 +96,6 @@ class Environment:
         self._io.done_bits, self._io.reset_bits, self._io.error_bits = self._ptr(_DONE), self._ptr(_RESET), self._ptr(_ERR)
         self._passable_key = None
         self._passable = None
-        self._rows = self._cols = 0      # shape of np_game as _sync_world last saw it
         self._ragged = False             # size_game is not the grid's shape (non-square game_size)
         self._sails = False              # set by _encode for a move outside ShipMove: its target is not ground
         self._w_game = self._w_ports = self._w_fuel = self._w_cargo = None   # what _sync_world last saw
@@ -140,8 +140,7 @@ class Environment:
             # x by size_game[0] and x indexes rows (:53, :99-100, :293).  The cells a ship can ever stand on are those
             # inside both, which is what the device gets as its map; a move that passes _is_within_map but leaves the
             # array raises numpy's IndexError in the reference, and in step() here before anything is launched.
-            self._rows, self._cols = int(g.shape[0]), int(g.shape[1])
-            wd, hd = min(int(self.size_game[0]), self._rows), min(int(self.size_game[1]), self._cols)
+            wd, hd = min(int(self.size_game[0]), int(g.shape[0])), min(int(self.size_game[1]), int(g.shape[1]))
             self._ragged = (wd, hd) != (int(self.size_game[0]), int(self.size_game[1]))
             self._passable = np.ascontiguousarray(g[:wd, :hd] != Entity.GROUND, dtype=np.uint8)
             self._passable_bytes = self._passable.tobytes()
