@@ -253,32 +253,63 @@ __device__ __forceinline__ uint32_t range_bits(int lo, int hi, int wi) {
   return (b == 32 ? 0xFFFFFFFFu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
 }
 
+// What the mask of a ship standing on port k adds to the four moves -- amounts 1..stock of cargo and of fuel
+// (:159-173) -- is the same for every ship on that port: one row of `words` words per port, built once per CTA.  A
+// thread then scans the P ports once (first match = the port the ship is at, every other match that is not its
+// origin is selectable, :141-156), ORs the select bits into the row and parks it in a shared [256, words] tile that
+// the CTA writes out as one contiguous block (a thread's own `words` words lie 36 bytes from its neighbour's).
+constexpr int kValidMaxWords = (4 + kMaxPorts + SHIPENV_N_CARGO_ACTIONS + SHIPENV_N_FUEL_ACTIONS + 31) / 32;   // 9
+
 __global__ void __launch_bounds__(kThreads) valid_actions_kernel(const ValidArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t world_bar;
+  __shared__ uint32_t port_row[kMaxPorts][kValidMaxWords];
+  __shared__ __align__(16) uint32_t tile_s[kThreads * kValidMaxWords];   // [256, words], the layout of the output
+                                                  // (words = 9 for P >= 3: an odd stride, the row writes do not conflict)
   stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
-  const int P = w.h->P;
+  const int P = w.h->P, words = a.words;
+  const int c0 = 4 + P + 1, f0 = 4 + P + SHIPENV_N_CARGO_ACTIONS + 1;   // the first amount is 1
+  for (int e = threadIdx.x; e < P * words; e += kThreads) {
+    const int k = e / words, wi = e - k * words;
+    const uint32_t p = w.h->port[k];
+    const int n_cargo = min(int(p >> 24), SHIPENV_N_CARGO_ACTIONS - 1);
+    const int n_fuel = min(int((p >> 16) & 255u), SHIPENV_N_FUEL_ACTIONS - 1);
+    port_row[k][wi] = range_bits(c0, c0 + n_cargo, wi) | range_bits(f0, f0 + n_fuel, wi);
+  }
+  __syncthreads();
   const int64_t n_tiles = (a.n + kThreads - 1) / kThreads;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t i = tile * kThreads + threadIdx.x;
-    if (i >= a.n) continue;
-    const ShipR s = unpack(a.ships[i]);
-    const uint32_t key = uint32_t(s.x) | (uint32_t(s.y) << 8);
-    uint32_t select = 0;                              // bit k: port k selectable (:141-156)
-    for (int k = 0; k < P; ++k)
-      if (k != s.origin && (w.h->port[k] & 0xFFFFu) == key) select |= 1u << k;
-    const int cur = current_port(w, s);                // :159-173
-    const int n_cargo = cur >= 0 ? min(int(w.h->port[cur] >> 24), SHIPENV_N_CARGO_ACTIONS - 1) : 0;
-    const int n_fuel = cur >= 0 ? min(int((w.h->port[cur] >> 16) & 255u), SHIPENV_N_FUEL_ACTIONS - 1) : 0;
-    const int c0 = 4 + P + 1, f0 = 4 + P + SHIPENV_N_CARGO_ACTIONS + 1;   // first amount is 1
-    for (int wi = 0; wi < a.words; ++wi) {
-      uint32_t m = range_bits(0, 4, wi);               // the four moves are always valid (:137-139)
-      m |= range_bits(c0, c0 + n_cargo, wi) | range_bits(f0, f0 + n_fuel, wi);
-      for (int k = 0; k < P; ++k)
-        if ((select >> k) & 1u) m |= range_bits(4 + k, 5 + k, wi);
-      a.mask[i * a.words + wi] = m;
+    if (i < a.n) {
+      const uint4 rec = a.ships[i];
+      const uint32_t key = rec.x & 0xFFFFu, origin = (rec.x >> 16) & 255u;
+      uint64_t select = 0;                              // bit 4 + k: port k selectable
+      int cur = -1;
+      for (int k = P - 1; k >= 0; --k) {
+        const bool here = (w.h->port[k] & 0xFFFFu) == key;
+        if (here) cur = k;                             // ends on the first match (_get_current_port_idx, :145-153)
+        if (here && uint32_t(k) != origin) select |= 1ull << (4 + k);
+      }
+      uint32_t* row = tile_s + threadIdx.x * words;
+      for (int wi = 0; wi < words; ++wi) {
+        uint32_t m = cur >= 0 ? port_row[cur][wi] : 0u;
+        if (wi == 0) m |= 0xFu | uint32_t(select);     // the four moves are always valid (:137-139)
+        if (wi == 1) m |= uint32_t(select >> 32);
+        row[wi] = m;
+      }
     }
+    __syncthreads();
+    const int64_t base = tile * kThreads;
+    const int live = int(min(int64_t(kThreads), a.n - base));
+    uint32_t* out = a.mask + base * words;
+    if (live == kThreads && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {          // the tile as 16-byte pieces
+      for (int j = threadIdx.x; j < kThreads * words / 4; j += kThreads)
+        reinterpret_cast<uint4*>(out)[j] = reinterpret_cast<const uint4*>(tile_s)[j];
+    } else {
+      for (int j = threadIdx.x; j < live * words; j += kThreads) out[j] = tile_s[j];
+    }
+    __syncthreads();
   }
 }
 
