@@ -324,14 +324,33 @@ __device__ __forceinline__ int bucket(double v, double width) {   // min(int(v /
 
 __global__ void __launch_bounds__(kThreads) discretize_kernel(const uint4* __restrict__ ships, int16_t* __restrict__ keys,
                                                               int64_t n) {
-  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kThreads) {
-    const ShipR s = unpack(ships[i]);
-    int16_t* k = keys + i * 6;
-    k[0] = int16_t(s.x); k[1] = int16_t(s.y);
-    k[2] = int16_t(bucket(s.fuel, 10.0));      // the state dict's "cargo" is fuel (shipping/environment.py:206)
-    k[3] = int16_t(bucket(s.fuel, 20.0));
-    k[4] = s.origin == kNone ? int16_t(-1) : int16_t(s.origin);
-    k[5] = s.dest == kNone ? int16_t(-1) : int16_t(s.dest);
+  // a thread's six int16 lie 12 bytes from its neighbour's: the CTA parks its [256, 6] tile in shared memory and writes
+  // it out as one contiguous block of 16-byte pieces
+  __shared__ __align__(16) uint32_t tile_s[kThreads * 3];
+  const int64_t n_tiles = (n + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i = tile * kThreads + threadIdx.x;
+    if (i < n) {
+      const ShipR s = unpack(ships[i]);
+      const int k2 = bucket(s.fuel, 10.0);      // the state dict's "cargo" is fuel (shipping/environment.py:206)
+      const int k3 = bucket(s.fuel, 20.0);
+      const int k4 = s.origin == kNone ? -1 : s.origin, k5 = s.dest == kNone ? -1 : s.dest;
+      uint32_t* row = tile_s + threadIdx.x * 3;
+      row[0] = uint32_t(s.x) | (uint32_t(s.y) << 16);
+      row[1] = (uint32_t(k2) & 0xFFFFu) | (uint32_t(k3) << 16);
+      row[2] = (uint32_t(k4) & 0xFFFFu) | (uint32_t(k5) << 16);
+    }
+    __syncthreads();
+    const int64_t base = tile * kThreads;
+    const int live = int(min(int64_t(kThreads), n - base));
+    uint32_t* out = reinterpret_cast<uint32_t*>(keys + base * 6);
+    if (live == kThreads && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+      for (int j = threadIdx.x; j < kThreads * 3 / 4; j += kThreads)
+        reinterpret_cast<uint4*>(out)[j] = reinterpret_cast<const uint4*>(tile_s)[j];
+    } else {
+      for (int j = threadIdx.x; j < live * 3; j += kThreads) out[j] = tile_s[j];
+    }
+    __syncthreads();
   }
 }
 
