@@ -135,6 +135,35 @@ def test_preprocessing_helpers():
     assert map_action_to_env_action(258, E) == [ActionType.TAKE_FUEL, 199]
 
 
+def test_action_codes_match_the_header():
+    """The action-space constants of the Python layer are the header's, and the move code of any (dx, dy) is the one the
+    reference harness uses (oracle/ref_harness.py: move_xy) -- the four moves of ShipMove keep their flat indices."""
+    import re
+    from shippingenv_b200 import _native
+    from shippingenv_b200.preprocessing import move_action
+    from oracle.ref_harness import move_xy
+    hdr = open(os.path.join(ROOT, "include", "shipenv.h")).read()
+    macro = {m.group(1): m.group(2) for m in re.finditer(r"#define (SHIPENV_\w+) \(?(-?\w+)\)?", hdr)}
+    assert int(macro["SHIPENV_ACT_POLICY"]) == _native.ACT_POLICY == -1
+    assert int(macro["SHIPENV_ACT_NONE"]) == _native.ACT_NONE == -32768
+    assert int(macro["SHIPENV_ACT_MOVE_XY_BASE"]) == _native.ACT_MOVE_XY_BASE == -2
+    assert int(macro["SHIPENV_MOVE_XY_MAX"]) == _native.MOVE_XY_MAX == 90
+    assert int(macro["SHIPENV_ACT_EXT_CARGO"], 16) == _native.ACT_EXT_CARGO
+    assert int(macro["SHIPENV_ACT_EXT_FUEL"], 16) == _native.ACT_EXT_FUEL
+    assert [move_action(*m) for m in ((0, -1), (-1, 0), (0, 1), (1, 0))] == [0, 1, 2, 3]
+    seen = set()
+    for dx in (-90, -7, -1, 0, 1, 2, 90):
+        for dy in (-90, -3, -1, 0, 1, 5, 90):
+            if abs(dx) + abs(dy) == 1:
+                continue
+            a = move_action(dx, dy)
+            assert a == move_xy(dx, dy) and -32762 <= a <= -2 and a not in seen
+            seen.add(a)
+    assert move_action(0, 0) == -2 - (90 * 181 + 90) and move_action(90, 90) == -32762 and move_action(-90, -90) == -2
+    with pytest.raises(ValueError):
+        move_action(91, 0)
+
+
 def test_shard_ranges_partition_the_env_ids():
     from shippingenv_b200.stats import shard_range
     for total in (16, 17, 1 << 24, 5):
