@@ -153,6 +153,9 @@ def test_steps_on_arbitrary_worlds(seed, W, H, P, density, n, lean):
     for t in range(8):
         kind = rng.random(n)
         acts = np.where(kind < 0.5, rng.integers(0, 4, n), np.where(kind < 0.75, -1, rng.integers(0, n_act + 2, n)))
+        # moves by any (dx, dy) (-2 - ((dx+90)*181 + (dy+90))): short ones that mostly stay on the map, and any code
+        free = -2 - ((rng.integers(-4, 5, n) + 90) * 181 + (rng.integers(-4, 5, n) + 90))
+        acts = np.where(kind > 0.9, free, np.where(kind > 0.88, rng.integers(-32768, -1, n), acts))
         acts = acts.astype(np.int16)
         a = torch.from_numpy(acts).cuda()
         if lean:
