@@ -11,7 +11,6 @@ ap.add_argument("--roots", type=int, default=65536)
 ap.add_argument("--sims", type=int, default=50)
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--reps", type=int, default=10)
-ap.add_argument("--check", type=int, default=0, help="verify this many roots against the CPU oracle")
 args = ap.parse_args()
 z = np.load(os.path.join(ROOT, "tests", "golden", "default_map.npz"))
 R = args.roots
@@ -31,14 +30,3 @@ ms = e0.elapsed_time(e1) / args.reps
 steps = int(out["steps"].sum().item())
 print(f"rollouts: {R} roots x {args.sims} sims x <={args.steps} steps: {ms:.3f} ms/launch, {steps/ms/1e6:.2f} G rollout-steps/s, "
       f"{R/ms*1e3:.3e} roots/s, mean return {out['returns'].mean().item():.4f}, status!=0: {int((out['status'] != 0).sum())}")
-if args.check:
-    from oracle import lib as orc
-    o = orc.Oracle(z["passable"], env.ports, env.port_fuel, env.port_cargo)
-    roots, _ = env.state_numpy()
-    k = args.check
-    t0 = time.perf_counter()
-    want, fin, st, status = o.rollout(roots.view(orc.SHIP_DTYPE).reshape(-1)[:k], args.sims, args.steps, 0x5EED)
-    dt = time.perf_counter() - t0
-    got = out["returns"][:k].cpu().numpy()
-    assert (got.view(np.uint64) == want.view(np.uint64)).all()
-    print(f"oracle check ok on {k} roots; oracle {st.sum()/dt/1e6:.1f} M rollout-steps/s on 1 thread")
