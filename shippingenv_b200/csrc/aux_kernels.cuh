@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
 struct ObserveArgs {
   const void* world; uint32_t world_bytes;
   const uint4* ships; float* obs; int64_t n; int obs_width;
+  int bufs;   // row tiles in shared memory: 2 (the bulk store of one drains while the next is assembled), 1 with many ports
 };
 
 __global__ void __launch_bounds__(kThreads) observe_kernel(const ObserveArgs a) {
@@ -45,12 +46,17 @@ __global__ void __launch_bounds__(kThreads) observe_kernel(const ObserveArgs a) 
   stage_world(smem, a.world, a.world_bytes, &world_bar);
   const WorldView w(smem);
   const int width = a.obs_width, tid = threadIdx.x;
-  float* tile = reinterpret_cast<float*>(smem + ((a.world_bytes + 127u) & ~127u));
-  for (int c = 6; c < width; ++c) tile[size_t(tid) * width + c] = w.h->obs_tail[c - 6];
+  float* tiles = reinterpret_cast<float*>(smem + ((a.world_bytes + 127u) & ~127u));   // a.bufs tiles of [256, width]
+  for (int b = 0; b < a.bufs; ++b)
+    for (int c = 6; c < width; ++c) tiles[(size_t(b) * kThreads + tid) * width + c] = w.h->obs_tail[c - 6];
   const int64_t n_tiles = (a.n + kThreads - 1) / kThreads;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  int buf = 0;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= a.bufs - 1) {
+    float* tile = tiles + size_t(buf) * kThreads * width;
     const int64_t i = t * kThreads + tid;
-    if (tid == 0) tma_store_wait_read<0>();
+    if (tid == 0) {                                // the store that last used this tile has read it
+      if (a.bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+    }
     __syncthreads();
     if (i < a.n) obs_head(unpack(a.ships[i]), tile + size_t(tid) * width);
     fence_proxy_async();

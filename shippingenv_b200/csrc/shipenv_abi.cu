@@ -841,8 +841,11 @@ int shipenv_observe(shipenv_ctx* c, const shipenv_ship* ships, float* obs, int64
   DeviceGuard guard(c->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = sync_world(c, stream)) return rc;
-  ObserveArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(ships), obs, n, 6 + 4 * c->P};
-  const size_t smem = ((size_t(c->world_bytes) + 127) & ~size_t(127)) + size_t(kThreads) * a.obs_width * 4;
+  ObserveArgs a{c->d_world, c->world_bytes, reinterpret_cast<const uint4*>(ships), obs, n, 6 + 4 * c->P, 2};
+  const size_t tile_bytes = size_t(kThreads) * a.obs_width * 4;
+  const size_t world_smem = (size_t(c->world_bytes) + 127) & ~size_t(127);
+  if (world_smem + 2 * tile_bytes > size_t(c->max_smem_optin) / 2) a.bufs = 1;   // many ports: one tile, and two CTAs per SM
+  const size_t smem = world_smem + size_t(a.bufs) * tile_bytes;
   int grid = 0;
   if (int rc = grid_for(c, observe_kernel, c->occ_observe, kThreads, smem, (n + kThreads - 1) / kThreads, &grid)) return rc;
   observe_kernel<<<grid, kThreads, smem, stream>>>(a);
