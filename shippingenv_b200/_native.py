@@ -160,6 +160,7 @@ class Context:
         h = C.c_void_p()
         check(lib().shipenv_ctx_create(self.device, C.byref(h)))
         self._h = h
+        self._h_int = h.value                  # the handle as a plain int (read by the C fast path of the facade)
         self._serve = lib().shipenv_serve_step
         self.P = -1
         self.shape = None

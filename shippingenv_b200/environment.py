@@ -50,6 +50,32 @@ _FLAGS_FMT = struct.Struct("<IIIBxhB")           # done, reset, error words, sta
 # SHIPENV_NO_SERVER=1: every step() is one shipenv_step_sample launch + one stream synchronisation (A/B, debugging)
 _USE_SERVER = os.environ.get("SHIPENV_NO_SERVER") != "1"
 
+# The hot calls in C (csrc/facade_fast.c -> _facade_fast.so, built by __graft_entry__.build()): step() and the
+# look-ahead sample_action() for the common shapes of a call; it declines everything else and the Python below runs,
+# which stays the complete implementation.  SHIPENV_NO_FASTPATH=1 (or a missing .so) keeps it out.
+_fast = None
+_fast_tried = False
+
+
+def _bind_fast():
+    """Load and bind the C fast path once (needs libshipenv.so: its shipenv_serve_step is what the C code calls)."""
+    global _fast, _fast_tried
+    if _fast_tried:
+        return
+    _fast_tried = True
+    if not _USE_SERVER or os.environ.get("SHIPENV_NO_FASTPATH") == "1":
+        return
+    try:
+        import ctypes
+        from . import _facade_fast as mod
+        addr = ctypes.cast(nat.lib().shipenv_serve_step, ctypes.c_void_p).value
+        mod.bind(addr, _ERRORS, nat.check, MOVES, nat.N_CARGO_ACTIONS, nat.N_FUEL_ACTIONS, nat.ACT_EXT_CARGO,
+                 nat.ACT_EXT_FUEL)
+        _fast = mod
+    except ImportError:
+        _fast = None
+
+
 _contexts = {}   # device index -> (Context, world signature currently uploaded)
 
 
@@ -78,6 +104,7 @@ class Environment:
         self._device = torch.device(device if device is not None else "cuda")
         if self._device.index is None:
             self._device = torch.device("cuda", torch.cuda.current_device())
+        _bind_fast()
         self._seed = _pyrandom.getrandbits(64) if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
         self._env_id = int(env_id)
         self._clock = 0          # episode << 16 | step: selects the Philox cell of the next step
@@ -235,6 +262,10 @@ class Environment:
                 self._clock, self._word, self._world_sig) if len(pos) == 2 else None
 
     def sample_action(self):
+        if _fast is not None:
+            r = _fast.sample_action(self)
+            if r is not NotImplemented:
+                return r
         ctx = self._sync_world()
         spec, self._spec = self._spec, None
         if spec is not None and spec == self._snapshot():
@@ -325,6 +356,10 @@ class Environment:
                          "boolean arrays are valid indices")
 
     def step(self, action):
+        if _fast is not None:
+            r = _fast.step(self, action)
+            if r is not NotImplemented:
+                return r
         if len(self.port_positions) == 0:
             raise Exception("No ports available")                                     # :360
         a = self._encode(action)

@@ -116,16 +116,42 @@ class _TorchForFacade:
         return _Pinnable(torch.zeros(*a, **k))
 
 
-def install():
-    """Patch the facade module so that it runs without a GPU.  Returns the dict of fake contexts (per device)."""
+_keep = []          # ctypes callbacks must outlive the C code that holds their address
+
+
+def install(fast=None):
+    """Patch the facade module so that it runs without a GPU.  Returns the dict of fake contexts (per device).
+    ``fast``: True = the facade's C fast path (csrc/facade_fast.c) is bound to a callback that lets the oracle answer
+    ``shipenv_serve_step`` (so the C code itself is exercised on a CPU box), False = Python only, None = the
+    environment decides (SHIPENV_NO_FASTPATH)."""
     contexts = {}
+    by_handle = {}
 
     def context(device_index):
         if device_index not in contexts:
-            contexts[device_index] = [OracleContext(device_index), None]
+            ctx = OracleContext(device_index)
+            ctx._h_int = 0x1000 + device_index            # what the C fast path passes back as the context handle
+            by_handle[ctx._h_int] = ctx
+            contexts[device_index] = [ctx, None]
         return contexts[device_index]
 
     E._context = context
     E.torch = _TorchForFacade()
     E.nat.host_device_pointer = lambda host_ptr: host_ptr
+    import os
+    if fast is None:
+        fast = os.environ.get("SHIPENV_NO_FASTPATH") != "1"
+    E._fast, E._fast_tried = None, True                   # never the real shipenv_serve_step on this box
+    if fast:
+        from shippingenv_b200 import _facade_fast as mod
+
+        @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32)
+        def serve(handle, block, seed, env_id, max_steps, flags, word0):
+            by_handle[handle].serve_step(block, seed, env_id, max_steps, flags, word0)
+            return 0
+
+        _keep.append(serve)
+        mod.bind(C.cast(serve, C.c_void_p).value, E._ERRORS, nat.check, E.MOVES, nat.N_CARGO_ACTIONS,
+                 nat.N_FUEL_ACTIONS, nat.ACT_EXT_CARGO, nat.ACT_EXT_FUEL)
+        E._fast = mod
     return contexts

@@ -113,6 +113,18 @@ def test_facade_free_moves_and_nonsquare_maps_like_the_reference():
     assert replay_facade_trace() == 804
 
 
+def test_c_fast_path_equals_the_python_path_on_the_kernels():
+    """tests/fastpath_diff.py with the real server kernel behind both: 3,000 random API calls on two facades, one through
+    the C fast path, one through Python only -- same results, exceptions and attributes after every call."""
+    import shippingenv_b200.environment as E
+    from fastpath_diff import diff
+    from shippingenv_b200 import Environment
+    Environment(os.path.join(GOLDEN, "default_map.npz"), seed=1)       # loads and binds the C module
+    if E._fast is None:
+        pytest.skip("the C fast path is not built or is disabled (SHIPENV_NO_FASTPATH / SHIPENV_NO_SERVER)")
+    assert diff(calls=3000, seed=5) == 3000
+
+
 def test_facade_crafted_states_and_policy_loop():
     """g6: attributes assigned from outside (as agents/mcts.py:199-208 does), then the reference's
     `a = sample_action(); try: step(a) except: continue` loop for policy rows."""
