@@ -31,7 +31,7 @@ static long g_n_cargo = 50, g_n_fuel = 200, g_ext_cargo = 0x4000, g_ext_fuel = 0
 /* interned attribute names */
 static PyObject *s_port_positions, *s_destination, *s_origin, *s_ship_position, *s_cargo, *s_fuel, *s_clock, *s_word,
     *s_seed, *s_env_id, *s_host_ptr, *s_ragged, *s_sync_world, *s_h_int, *s_spec, *s_world_sig, *s_np_game,
-    *s_build_state;
+    *s_build_state, *s_slot, *s_w_game, *s_w_ports, *s_w_fuel, *s_w_cargo, *s_port_fuel, *s_port_cargo;
 
 /* offsets inside shipenv_host_block (include/shipenv.h) */
 enum { OFF_SHIP = 0, OFF_REWARD = 16, OFF_CLOCK = 32, OFF_ACTION = 48, OFF_DONE = 64, OFF_STATUS = 76, OFF_NEXT = 84 };
@@ -95,8 +95,44 @@ static int raise_status(long status) {
   return -1;
 }
 
+/* The fast path of Environment._sync_world(): the same grid object, the same port tables, and the context still holds
+ * this world.  1 = yes (*handle set), 0 = no / cannot tell (the Python method decides), -1 = error. */
+static int world_unchanged(PyObject *env, uint64_t *handle) {
+  int ok = 0;
+  PyObject *slot = NULL, *sig = NULL, *a = NULL, *b = NULL, *h = NULL;
+  slot = PyObject_GetAttr(env, s_slot);
+  if (!slot) return -1;
+  sig = PyObject_GetAttr(env, s_world_sig);
+  if (!sig) goto out_err;
+  if (!PyList_CheckExact(slot) || PyList_GET_SIZE(slot) != 2 || sig == Py_None || PyList_GET_ITEM(slot, 1) != sig) goto out;
+  a = PyObject_GetAttr(env, s_np_game); b = PyObject_GetAttr(env, s_w_game);
+  if (!a || !b) goto out_err;
+  if (a != b) goto out;
+  PyObject *cur[3] = {s_port_positions, s_port_fuel, s_port_cargo}, *seen[3] = {s_w_ports, s_w_fuel, s_w_cargo};
+  for (int k = 0; k < 3; ++k) {
+    Py_CLEAR(a); Py_CLEAR(b);
+    a = PyObject_GetAttr(env, cur[k]); b = PyObject_GetAttr(env, seen[k]);
+    if (!a || !b) goto out_err;
+    const int eq = PyObject_RichCompareBool(a, b, Py_EQ);
+    if (eq < 0) goto out_err;
+    if (!eq) goto out;
+  }
+  h = PyObject_GetAttr(PyList_GET_ITEM(slot, 0), s_h_int);
+  if (!h) { PyErr_Clear(); goto out; }
+  ok = as_u64(h, handle) == 0 && *handle != 0;
+out:
+  Py_XDECREF(slot); Py_XDECREF(sig); Py_XDECREF(a); Py_XDECREF(b); Py_XDECREF(h);
+  return ok;
+out_err:
+  Py_XDECREF(slot); Py_XDECREF(sig); Py_XDECREF(a); Py_XDECREF(b); Py_XDECREF(h);
+  return -1;
+}
+
 /* env._sync_world() -> the context's handle (0 = could not be had: decline) */
 static int context_handle(PyObject *env, uint64_t *handle) {
+  const int same = world_unchanged(env, handle);
+  if (same < 0) return -1;
+  if (same) return 0;
   PyObject *ctx = PyObject_CallMethodNoArgs(env, s_sync_world);
   if (!ctx) return -1;                              /* its exception propagates */
   PyObject *h = PyObject_GetAttr(ctx, s_h_int);
@@ -375,5 +411,7 @@ PyMODINIT_FUNC PyInit__facade_fast(void) {
   INTERN(s_env_id, "_env_id"); INTERN(s_host_ptr, "_host_ptr"); INTERN(s_ragged, "_ragged");
   INTERN(s_sync_world, "_sync_world"); INTERN(s_h_int, "_h_int"); INTERN(s_spec, "_spec");
   INTERN(s_world_sig, "_world_sig"); INTERN(s_np_game, "np_game"); INTERN(s_build_state, "_build_state");
+  INTERN(s_slot, "_slot"); INTERN(s_w_game, "_w_game"); INTERN(s_w_ports, "_w_ports"); INTERN(s_w_fuel, "_w_fuel");
+  INTERN(s_w_cargo, "_w_cargo"); INTERN(s_port_fuel, "port_fuel"); INTERN(s_port_cargo, "port_cargo");
   return PyModule_Create(&module);
 }

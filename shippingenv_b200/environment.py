@@ -126,6 +126,7 @@ class Environment:
         self._ragged = False             # size_game is not the grid's shape (non-square game_size)
         self._sails = False              # set by _encode for a move outside ShipMove: its target is not ground
         self._w_game = self._w_ports = self._w_fuel = self._w_cargo = None   # what _sync_world last saw
+        self._slot = None
 
     # ------------------------------------------------------------------ construction
     def _is_within_map(self, x, y):
@@ -182,6 +183,7 @@ class Environment:
             slot[0].set_ports(ports, list(map(int, self.port_fuel)), list(map(int, self.port_cargo)))
             slot[1] = sig
         self._world_sig = slot[1]
+        self._slot = slot                # (read by the C fast path, which makes the check above itself)
         self._w_game = self.np_game
         self._w_ports = [list(p) for p in self.port_positions]
         self._w_fuel, self._w_cargo = list(self.port_fuel), list(self.port_cargo)

@@ -30,6 +30,11 @@ def diff(calls=6000, seed=11):
         for p in [[41, 40], [60, 22], [78, 29], [49, 72], [62, 72]]:
             e.add_port(list(p))
         envs.append(e)
+    # a third facade with another world on the same device: its calls replace the world the context holds
+    intruder = Environment(os.path.join(HERE, "golden", "default_map.npz"), seed=99)
+    for p in [[41, 40], [60, 22], [49, 72]]:
+        intruder.add_port(list(p))
+    intruder.reset()
     served = declined = 0
 
     def both(fn):
@@ -73,7 +78,7 @@ def diff(calls=6000, seed=11):
         elif u < 0.90:
             both(lambda e: e.reset())
         else:                                          # attributes assigned from outside
-            k = int(rng.integers(0, 8))
+            k = int(rng.integers(0, 11))
             port = [[41, 40], [60, 22], [78, 29], [49, 72], [62, 72]][int(rng.integers(0, 5))]
             for e in envs:
                 if k == 0:
@@ -90,8 +95,17 @@ def diff(calls=6000, seed=11):
                     e.ship_position = tuple(port)          # a tuple: the C code declines, Python handles it
                 elif k == 6:
                     e.ship_position = [int(rng.integers(0, 100)), int(rng.integers(0, 100))] if c % 2 else list(port)
-                else:
+                elif k == 7:
                     e.port_cargo = list(e.port_cargo)      # a new list object, same contents
+                elif k == 8:
+                    e.port_cargo[int(c) % 5] = 5 + int(c) % 16      # the stock changed in place: a new world
+                elif k == 9:
+                    e.port_fuel = [20, 14, 18, 12, 16 + int(c) % 3]
+            if k == 10:                                # another facade steps in between: the device's world changes
+                try:
+                    intruder.step(intruder.sample_action())
+                except Exception:                      # noqa: BLE001
+                    pass
             if k == 6:                                 # both envs must see the same random position
                 envs[1].ship_position = list(envs[0].ship_position)
             assert _state(envs[0]) == _state(envs[1])
