@@ -200,6 +200,9 @@ __global__ void __launch_bounds__(32) step_server_kernel(const __grid_constant__
       continue;
     }
     last = seq;
+#ifdef SHIPENV_SERVER_TIMING
+    const unsigned long long t_seen = global_timer_ns();
+#endif
     if (__shfl_sync(0xFFFFFFFFu, v, kSrvCmd) == kSrvCmdQuit) { quit = true; break; }
     uint4 rec;
     rec.x = __shfl_sync(0xFFFFFFFFu, v, 0); rec.y = __shfl_sync(0xFFFFFFFFu, v, 1);
@@ -229,9 +232,16 @@ __global__ void __launch_bounds__(32) step_server_kernel(const __grid_constant__
                  ((o.flags & kFlagError) ? 1u << 26 : 0u);
       out_s[6] = uint32_t(__double2loint(o.reward)); out_s[7] = uint32_t(__double2hiint(o.reward));
       out_s[8] = uint32_t(uint16_t(int16_t(next)));
+#ifdef SHIPENV_SERVER_TIMING
+      out_s[9] = uint32_t(global_timer_ns() - t_seen);      // ns from seeing the request to having the answer
+#endif
     }
     __syncwarp();
+#ifdef SHIPENV_SERVER_TIMING
+    if (lane >= 16 && lane < 16 + 10) st_volatile_u32(a.mailbox + lane, out_s[lane - 16]);
+#else
     if (lane >= 16 && lane < 16 + 9) st_volatile_u32(a.mailbox + lane, out_s[lane - 16]);
+#endif
     __threadfence_system();                          // the answer before its sequence number
     if (lane == 0) st_volatile_u32(a.mailbox + kSrvAck, seq);
     t_idle = global_timer_ns();

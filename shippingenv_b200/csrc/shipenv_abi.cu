@@ -809,6 +809,9 @@ int shipenv_serve_step(shipenv_ctx* c, shipenv_host_block* block, uint64_t seed,
   const uint64_t rbits = uint64_t(m[22]) | (uint64_t(m[23]) << 32);
   memcpy(&block->reward, &rbits, 8);
   block->next_action = int16_t(uint16_t(m[24]));
+#ifdef SHIPENV_SERVER_TIMING
+  memcpy(block->pad5, const_cast<const uint32_t*>(&m[25]), 4);      // tuning builds: the kernel's own time for the request, ns
+#endif
   return 0;
 }
 
